@@ -1,0 +1,116 @@
+/* trace_b200 -- C ABI of the B200-native TRACE inference hot path.
+ *
+ * The reference (gyxxyg/TRACE) is pure Python on top of `transformers`; it has no C/FFI/plugin seam
+ * (SURVEY.md §8(b)).  The drop-in boundary of this repo is therefore the reference's Python surface
+ * (trace_b200/model/…, mirroring trace/model/language_model/trace_mistral.py, trace/mm_utils.py,
+ * trace/conversation.py) and THIS header is the thin C ABI that surface calls through ctypes.  Each entry
+ * point states which reference call site it replaces.  See INTEGRATION.md for the binding a reference
+ * maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; trace_b200_last_error() returns a
+ * thread-local message.  All `dev` pointers are raw CUDA device pointers into caller-owned storage (e.g.
+ * torch tensors); `stream` is a cudaStream_t passed as void*.  One context per device, one caller thread
+ * per context (the reference is single-threaded, default stream).  No torch types appear here.
+ */
+#ifndef TRACE_B200_H_
+#define TRACE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRACE_B200_ABI_VERSION 1
+#define TRACE_B200_PAGE_SIZE 64          /* KV-cache positions per page */
+#define TRACE_B200_MAX_DECODE_BATCH 8
+#define TRACE_B200_NUM_SLOTS 8           /* SpatialSlotPool num_slots (multimodal_projector/builder.py:413) */
+
+typedef struct trace_b200_ctx trace_b200_ctx;
+
+/* Architecture = the keys of a TRACE checkpoint's config.json (SURVEY.md §5 "Config / flags") plus
+ * workspace sizing. */
+typedef struct trace_b200_config {
+  /* CLIP vision tower (HF CLIPVisionConfig) */
+  int32_t vit_width, vit_heads, vit_layers, vit_mlp, image_size, patch_size;
+  float vit_ln_eps;
+  /* Mistral decoder (HF MistralConfig) */
+  int32_t hidden, layers, heads, kv_heads, head_dim, ffn, vocab;
+  float rope_theta, rms_eps;
+  /* workspaces */
+  int32_t vit_chunk_frames;     /* frames encoded per ViT pass (activations stay L2-resident) */
+  int32_t max_prefill_tokens;   /* B*S upper bound for one prefill call */
+  int32_t max_ctx;              /* positions per sequence (prefill + generated) */
+  int32_t kv_pages;             /* pages in the KV pool */
+} trace_b200_config;
+
+int trace_b200_abi_version(void);
+const char* trace_b200_last_error(void);
+
+/* Lifetime.  create() allocates every workspace and the KV pool; nothing is allocated afterwards. */
+int trace_b200_create(const trace_b200_config* cfg, int device, trace_b200_ctx** out);
+void trace_b200_destroy(trace_b200_ctx* ctx);
+
+/* Weights: HF state-dict names exactly as the reference checkpoint stores them (SURVEY.md §4 state-dict
+ * table; replaces TraceMistralForCausalLM.from_pretrained, trace/model/builder.py:114).  fp16 only
+ * (builder.py:50 torch_dtype=float16).  The tensor is copied (and re-packed: fused QKV, interleaved
+ * gate/up, padded patch kernel, stacked heads) into engine-owned memory. */
+int trace_b200_load_weight(trace_b200_ctx* ctx, const char* hf_name, const void* dev_ptr, const int64_t* shape,
+                           int ndim, void* stream);
+int trace_b200_finalize_weights(trace_b200_ctx* ctx);   /* fails listing the first missing tensor */
+
+/* encode_images_or_videos up to the projector (trace_arch.py:218-235): CLIPVisionTower.forward +
+ * feature_select (clip_encoder.py:31-53, hidden_states[-2] without CLS) + SpatialSlotPool.forward
+ * (multimodal_projector/builder.py:427-467).
+ *   pixels  [F,3,H,W] fp16 (CLIP-normalised)       -> slots_out [F,8,hidden] fp16
+ *   feats_out (optional, may be NULL) [F,patches,vit_width] fp16 receives the CLIP features. */
+int trace_b200_encode_frames(trace_b200_ctx* ctx, const void* pixels, int F, void* slots_out, void* feats_out,
+                             void* stream);
+
+/* prepare_inputs_labels_for_multimodal, prefill branch (trace_arch.py:377-426) + the time rows of
+ * encode_images_or_videos (trace_arch.py:237-258).  ids [B,L] int64 with exactly one -201 per row and -205
+ * for <sync>; slots [B*T*8, hidden]; time_ids [B,T,6] int32 (host-formatted '0>6.1f' ids, time_encoder.py:58).
+ * embeds_out [B, L-1+14T, hidden] fp16. */
+int trace_b200_build_prefill(trace_b200_ctx* ctx, const int64_t* ids_dev, int B, int L, int T, const void* slots,
+                             const int32_t* time_ids_dev, void* embeds_out, void* stream);
+
+/* KV slots (replaces HF DynamicCache): a slot owns ceil(n_positions/64) pages until freed. */
+int trace_b200_alloc_slot(trace_b200_ctx* ctx, int n_positions, int* slot_out);
+int trace_b200_free_slot(trace_b200_ctx* ctx, int slot);
+
+/* Step 0 of generate: MistralModel prefill over inputs_embeds (trace_mistral.py:178-188), all-ones
+ * attention mask.  embeds [B,S,hidden] fp16; fills the slots' KV pages and keeps the last
+ * position's hidden state for trace_b200_decode.  hidden_out (optional) [B,S,hidden] receives the final
+ * (pre-norm) hidden states. */
+int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, const void* embeds, int S,
+                       void* hidden_out, void* stream);
+
+/* The greedy loop: heads + -inf mask + argmax (trace_mistral.py:190-252 + HF greedy), head switch
+ * (prepare_inputs_for_generation :336-344), decode-step embedding dispatch (trace_arch.py:345-375), decoder
+ * layers with KV append -- entirely on the device.  heads_inout_host[b] in {0,1,2} or -1 for "no heads given"
+ * (text head only, trace/__init__.py:infer); it is updated in place like the reference mutates `heads`.
+ * ids_out_host [B,max_new] int64 receives the NEW tokens only; *n_out = tokens per row (stops when every row
+ * hit EOS).  logits_out_dev (optional) [max_new,B,vocab+27] fp32 receives the masked logits of each step. */
+int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new,
+                      int eos, int pad, int64_t* ids_out_host, int* n_out, float* logits_out_dev, void* stream);
+
+/* Introspection used by bench.py: kernels launched by this context since creation, and bytes of weights. */
+int64_t trace_b200_launch_count(trace_b200_ctx* ctx);
+int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);
+
+/* ---- single-kernel entry points (unit-parity tests and micro-benchmarks) --------------------------- */
+int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                       const void* bias, const void* residual, int ldr, int act, int swiglu, void* stream);
+int trace_b200_op_layernorm(const void* x, const void* w, const void* b, float eps, void* out, int rows, int D,
+                            void* stream);
+int trace_b200_op_rmsnorm(const void* x, const void* w, float eps, void* out, int rows, int D, void* stream);
+int trace_b200_op_attention(const void* q, const void* k, const void* v, void* o, int seqlen, int q_stride,
+                            int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride,
+                            int heads, int group, int batch, int head_dim, int causal, float scale, void* stream);
+int trace_b200_op_gemv(const void* W, const void* x, void* out, int B, int N, int K, int pro, const void* gamma,
+                       float eps, int epi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACE_B200_H_ */

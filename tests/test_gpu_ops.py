@@ -1,0 +1,106 @@
+"""Single-kernel parity (through the C ABI) against plain fp32 PyTorch restatements of the same op.
+Floating-point kernels: the tolerance is stated per test (fp16 inputs/outputs, fp32 accumulation)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).half()
+
+
+def _close(got, want, rtol, atol, what):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    bound = atol + rtol * want.abs()
+    bad = err > bound
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; max abs err "
+                                 f"{float(err.max()):.4g}, max |want| {float(want.abs().max()):.4g}, "
+                                 f"first bad index {bad.nonzero()[0].tolist()}")
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 384, 128), (67, 6144, 512), (1000, 1024, 592), (5000, 1024, 1024),
+                                   (129, 512, 4096), (16, 4096, 128), (2015, 1024, 4096)])
+def test_gemm_plain(M, N, K):
+    from trace_b200 import engine as E
+    a, w = _rand((M, K), 1.0, 1), _rand((N, K), 0.05, 2)
+    out = E.op_gemm(a, w)
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().t()
+    _close(out, want, 2e-3, 2e-3 * float(want.abs().max()), f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogues():
+    from trace_b200 import engine as E
+    M, N, K = 777, 1024, 256
+    a, w, bias, res = _rand((M, K), 1.0, 3), _rand((N, K), 0.05, 4), _rand((N,), 0.5, 5), _rand((M, N), 1.0, 6)
+    base = a.float() @ w.float().t() + bias.float()
+    _close(E.op_gemm(a, w, bias=bias), base, 2e-3, 4e-3, "bias")
+    _close(E.op_gemm(a, w, bias=bias, act=1), base * torch.sigmoid(1.702 * base), 2e-3, 4e-3, "quick_gelu")
+    _close(E.op_gemm(a, w, bias=bias, residual=res), base + res.float(), 2e-3, 4e-3, "residual")
+    out = res.clone()
+    # in-place residual (out aliases residual) as the engine uses it
+    import ctypes
+    lib = E.load_library()
+    rc = lib.trace_b200_op_gemm(a.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, M, N, K, bias.data_ptr(), out.data_ptr(), N, 0, 0,
+                                torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.trace_b200_last_error()
+    _close(out, base + res.float(), 2e-3, 4e-3, "in-place residual")
+    g = a.float() @ w.float().t()
+    want = torch.nn.functional.silu(g[:, 0::2]) * g[:, 1::2]
+    _close(E.op_gemm(a, w, swiglu=True), want, 2e-3, 4e-3, "swiglu")
+
+
+def test_norms():
+    from trace_b200 import engine as E
+    for D in (128, 192, 1024, 4096):
+        x, w, b = _rand((333, D), 2.0, 7), (1 + 0.1 * _rand((D,), 1.0, 8).float()).half(), _rand((D,), 0.1, 9)
+        if D <= 1024:
+            want = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5)
+            _close(E.op_layernorm(x, w, b, 1e-5), want, 2e-3, 2e-3, f"layernorm D={D}")
+        xf = x.float()
+        want = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).half().float()
+        _close(E.op_rmsnorm(x, w, 1e-5), want, 1e-3, 1e-3, f"rmsnorm D={D}")
+
+
+@pytest.mark.parametrize("B,S,heads,kvh,hd,causal", [(3, 577, 2, 2, 64, False), (2, 17, 2, 2, 64, False),
+                                                     (2, 200, 32, 8, 128, True), (1, 67, 32, 8, 128, True),
+                                                     (1, 1000, 8, 2, 128, True)])
+def test_attention(B, S, heads, kvh, hd, causal):
+    from trace_b200 import engine as E
+    qkv = _rand((B, S, (heads + 2 * kvh) * hd), 1.0, 11)
+    out = E.op_attention(qkv, heads, kvh, hd, causal)
+    q = qkv[..., : heads * hd].float().view(B, S, heads, hd).transpose(1, 2)
+    k = qkv[..., heads * hd: (heads + kvh) * hd].float().view(B, S, kvh, hd).transpose(1, 2)
+    v = qkv[..., (heads + kvh) * hd:].float().view(B, S, kvh, hd).transpose(1, 2)
+    k, v = k.repeat_interleave(heads // kvh, 1), v.repeat_interleave(heads // kvh, 1)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    if causal:
+        s = s.masked_fill(torch.triu(torch.ones(S, S, device="cuda", dtype=torch.bool), 1), float("-inf"))
+    want = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, heads * hd)
+    _close(out, want, 5e-3, 5e-3, f"attention B{B} S{S} h{heads}/{kvh} d{hd} causal={causal}")
+
+
+@pytest.mark.parametrize("B,N,K", [(1, 4096, 4096), (3, 6144, 4096), (8, 4096, 14336), (2, 512, 256), (1, 4096, 512)])
+def test_gemv(B, N, K):
+    from trace_b200 import engine as E
+    w, x = _rand((N, K), 0.02, 21), _rand((B, K), 1.0, 22)
+    want = x.float() @ w.float().t()
+    _close(E.op_gemv(w, x), want, 2e-3, 2e-3 * float(want.abs().max()), "gemv plain")
+    res = _rand((B, N), 1.0, 23)
+    out = res.clone()
+    E.op_gemv(w, x, epi=1, out=out)
+    _close(out, want + res.float(), 2e-3, 4e-3, "gemv residual")
+    _close(E.op_gemv(w, x, epi=2), torch.nn.functional.silu(want[:, 0::2]) * want[:, 1::2], 2e-3, 2e-3, "gemv swiglu")
+    if K <= 4096:
+        gamma = (1 + 0.1 * _rand((K,), 1.0, 24).float()).half()
+        xf = x.float()
+        xn = gamma.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).half().float()
+        wantn = xn.half().float() @ w.float().t()
+        _close(E.op_gemv(w, x, gamma=gamma, eps=1e-5), wantn, 2e-3, 2e-3 * float(wantn.abs().max()), "gemv rmsnorm")

@@ -1,0 +1,306 @@
+// Tensor-core GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] · W[N,K]^T )
+//
+// A (activations) and W (nn.Linear weight, [out,in]) are both K-major fp16, exactly the layouts the
+// reference's F.linear call sites use (HF CLIP q/k/v/out/fc1/fc2, HF Mistral q/k/v/o/gate/up/down,
+// SpatialSlotPool.readout multimodal_projector/builder.py:467), so no transposes are ever materialised.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D boxes {64 x 128} (A) and {64 x BN} (W), SWIZZLE_128B,
+//              STAGES-deep ring guarded by full/empty mbarriers
+//   warp 1   : UMMA issuer   -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//              from shared-memory descriptors; accumulators live in TMEM (2 stages x BN fp32 columns)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b.x32 -> registers -> bias / quick_gelu / residual / SwiGLU ->
+//              fp16 -> 16-byte global stores; overlaps with the next tile's main loop through the
+//              tmem_full / tmem_empty barrier pair.
+// Roofline: tensor pipe. 2*M*N*K flop per launch.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 halves = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;       // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  const __half* bias;      // [N] or null
+  const __half* residual;  // [M, ldr] or null (added after bias/activation)
+  __half* out;             // [M, ldo]
+  int ldr, ldo;
+  int act;                 // 0 none, 1 quick_gelu
+  int swiglu;              // 1: columns are (gate,up) pairs -> N/2 outputs silu(gate)*up
+};
+
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               int M, int N, int K, EpiParams ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM;
+        const int n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 halves = 32 B along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                       // TMEM lane quarter == warp_id % 4
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BM;
+      const int n0 = (tile / tiles_m) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {                   // all TMEM reads of this stage are done -> release it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (col0 + j8 * 8 < N) {
+              uint4 b = *reinterpret_cast<const uint4*>(ep.bias + col0 + j8 * 8);
+              float2 f0 = unpack_half2(b.x), f1 = unpack_half2(b.y), f2 = unpack_half2(b.z), f3 = unpack_half2(b.w);
+              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+            }
+          }
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+        }
+        if (ep.swiglu) {
+          // (gate, up) column pairs -> 16 outputs at column col0/2
+          __half* op = ep.out + static_cast<size_t>(row) * ep.ldo + (col0 >> 1);
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            if (col0 + j8 * 16 < N) {
+              uint4 o;
+              o.x = pack_half2(silu(v[j8 * 16 + 0]) * v[j8 * 16 + 1], silu(v[j8 * 16 + 2]) * v[j8 * 16 + 3]);
+              o.y = pack_half2(silu(v[j8 * 16 + 4]) * v[j8 * 16 + 5], silu(v[j8 * 16 + 6]) * v[j8 * 16 + 7]);
+              o.z = pack_half2(silu(v[j8 * 16 + 8]) * v[j8 * 16 + 9], silu(v[j8 * 16 + 10]) * v[j8 * 16 + 11]);
+              o.w = pack_half2(silu(v[j8 * 16 + 12]) * v[j8 * 16 + 13], silu(v[j8 * 16 + 14]) * v[j8 * 16 + 15]);
+              *reinterpret_cast<uint4*>(op + j8 * 8) = o;
+            }
+          }
+        } else {
+          __half* op = ep.out + static_cast<size_t>(row) * ep.ldo + col0;
+          const __half* rp = ep.residual ? ep.residual + static_cast<size_t>(row) * ep.ldr + col0 : nullptr;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (col0 + j8 * 8 < N) {
+              if (rp != nullptr) {
+                uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+                float2 f0 = unpack_half2(b.x), f1 = unpack_half2(b.y), f2 = unpack_half2(b.z), f3 = unpack_half2(b.w);
+                v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+                v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+              }
+              uint4 o;
+              o.x = pack_half2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+              o.y = pack_half2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+              o.z = pack_half2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+              o.w = pack_half2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(op + j8 * 8) = o;
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// 2-D K-major fp16 tensor [rows, cols] with leading dimension ld (elements); box {64, box_rows}, 128B swizzle.
+int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  TB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  TB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
+  TB_CHECK((static_cast<int64_t>(ld) * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb_, int M, int N, int K, const EpiParams& ep, int num_sms,
+           cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb_, M, N, K, ep);
+  TB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, __half* out, int ldo, int M, int N, int K,
+             const __half* bias, const __half* residual, int ldr, int act, int swiglu, int num_sms,
+             cudaStream_t stream) {
+  TB_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  TB_CHECK(N % 8 == 0, "N must be a multiple of 8");
+  TB_CHECK(!(swiglu && (N % 16 != 0)), "SwiGLU epilogue needs N % 16 == 0");
+  TB_CHECK(ldo % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "output / residual pitch must be 16-byte aligned");
+  TB_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "output must be 16-byte aligned");
+  // Wide tiles when they fill the machine, narrower ones for small problems (fewer idle SMs).
+  const bool wide = (static_cast<int64_t>(ceil_div(M, BM)) * ceil_div(N, 256) >= num_sms) && (N % 256 == 0 || N > 1024);
+  CUtensorMap ta, tw;
+  if (make_tmap(&ta, A, M, K, lda, BM)) return 1;
+  if (make_tmap(&tw, W, N, K, ldw, wide ? 256 : 128)) return 1;
+  EpiParams ep{bias, residual, out, ldr, ldo, act, swiglu};
+  return wide ? launch<256>(ta, tw, M, N, K, ep, num_sms, stream) : launch<128>(ta, tw, M, N, K, ep, num_sms, stream);
+}
+
+}  // namespace tb

@@ -1,0 +1,86 @@
+// Host-callable launchers of the trace_b200 sm_100a kernels.  All pointers are device pointers, all
+// launchers are asynchronous on `stream` and return 0 on success (tb::get_error() has the message).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tb {
+
+// ---- gemm_tc.cu : tcgen05/TMEM/TMA GEMM  out = epi(A[M,K] · W[N,K]^T) ------------------------------------
+// act: 0 none, 1 quick_gelu.  swiglu: W rows are (gate,up) interleaved, out has N/2 columns.
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, __half* out, int ldo, int M, int N, int K,
+             const __half* bias, const __half* residual, int ldr, int act, int swiglu, int num_sms,
+             cudaStream_t stream);
+
+// ---- norm.cu ---------------------------------------------------------------------------------------------
+int layernorm_f16(const __half* x, int ldx, const __half* w, const __half* b, float eps, __half* out, int ldo,
+                  int rows, int D, cudaStream_t stream);
+int rmsnorm_f16(const __half* x, int ldx, const __half* w, float eps, __half* out, int ldo, int rows, int D,
+                cudaStream_t stream);
+
+// ---- vit.cu ----------------------------------------------------------------------------------------------
+// pixels [F,3,H,W] fp16 -> patches [F*P, Kp] (col = c*ps*ps + ky*ps + kx, zero padded to Kp)
+int vit_im2col(const __half* pixels, __half* out, int F, int image, int ps, int Kp, cudaStream_t stream);
+// h[f,0] = cls + pos[0]; h[f,1+p] = patch[f*P+p] + pos[1+p]; then pre-LayerNorm -> out [F*(P+1), D]
+int vit_embed_ln(const __half* patch, const __half* cls, const __half* pos, const __half* ln_w, const __half* ln_b,
+                 float eps, __half* out, int F, int P, int D, cudaStream_t stream);
+
+// ---- attention.cu : flash-style attention on mma.sync (legacy tensor path; tcgen05 version is round-2 work) ----
+// Q/K/V element pointers with row strides (elements) and per-batch strides; head h uses columns [h*HD, (h+1)*HD)
+// of Q/O and [(h/group)*HD, ...) of K/V.  HD in {64, 128}.
+int attention_fwd(const __half* Q, const __half* K, const __half* V, __half* O, int seqlen, int q_stride,
+                  int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride, int heads,
+                  int group, int batch, int head_dim, int causal, float scale, cudaStream_t stream);
+
+// ---- projector.cu : fused SpatialSlotPool up to the slot-weighted sums --------------------------------------
+// feats: rows of width D with pitch ld; frame f owns rows [f*frame_rows + row_off, +n).  res [F*8, D] fp16.
+int slot_pool_fused(const __half* feats, int ld, int frame_rows, int row_off, int n, int D, int F,
+                    const __half* ln_w, const __half* ln_b, float eps, const __half* slots /*[D,8]*/,
+                    const float* cos_tab, const float* sin_tab /*[n, D/2]*/, __half* res, cudaStream_t stream);
+
+// ---- splice.cu : prefill activation assembly (prompt splice + time rows) -------------------------------------
+int splice_prefill(const int64_t* ids /*[B,L]*/, int B, int L, int T, const __half* slots /*[B*T*8,H]*/,
+                   const int32_t* time_ids /*[B,T,6]*/, const __half* embed, const __half* time_tab,
+                   const __half* sync_tab, int vocab, int H, __half* out /*[B,S,H]*/, cudaStream_t stream);
+
+// ---- rope_kv.cu : prefill RoPE (in place on the fused qkv buffer) + paged KV write ---------------------------
+int rope_kv_prefill(__half* qkv /*[B*S, (heads+2*kvh)*hd]*/, int B, int S, int heads, int kvh, int hd,
+                    const float* cos_tab, const float* sin_tab /*[max_pos, hd/2]*/, __half* k_pool, __half* v_pool,
+                    const int32_t* block_table /*[slots,max_pages]*/, const int32_t* slot_ids /*[B]*/, int max_pages,
+                    int page_size, cudaStream_t stream);
+
+// ---- decode.cu -------------------------------------------------------------------------------------------
+struct DecodeState {           // device-resident generation state (no host round trips inside the loop)
+  int32_t* pos;                // [B] number of cached positions (== position id of the token being fed)
+  int32_t* heads;              // [B] active head 0 text / 1 time / 2 score ; -1 = text-only (no heads given)
+  int32_t* finished;           // [B]
+  int32_t* step;               // [1] tokens emitted so far
+  int32_t* done_step;          // [1] step count at which all rows were finished (0 = not yet)
+  int64_t* out_ids;            // [B, max_new]
+  int32_t* slot_ids;           // [B]
+  int max_new;
+};
+
+// out[b, n] = epi( W[n,:] · pro(x[b,:]) ), B <= 8, N % 16 == 0, K % 256 == 0.
+// pro: 0 none, 1 RMSNorm(gamma, eps).  epi: 0 store, 1 residual add in place, 2 SwiGLU pairs (out has N/2 cols).
+int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, int B, int N, int K, int pro,
+             const __half* gamma, float eps, int epi, cudaStream_t stream);
+
+// fused: RoPE(q,k) + KV append + split-KV attention + last-CTA combine -> attn_out [B, heads*hd]
+int attn_decode(const __half* qkv, int B, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
+                __half* k_pool, __half* v_pool, const int32_t* block_table, int max_pages, int page_size,
+                const DecodeState& st, int nsplit, int max_ctx, float* part_o, float* part_ml, int32_t* counters,
+                __half* attn_out, cudaStream_t stream);
+
+// final RMSNorm + active-head GEMV + masked argmax candidates.  Wh: packed [Npad, K] rows = global token ids.
+int head_gemv(const __half* Wh, const __half* x, int ldx, int B, int n_valid, int Npad, int K, const __half* gamma,
+              float eps, int vocab, const DecodeState& st, float* cand_val, int32_t* cand_idx,
+              float* logits_out /*[B, n_valid] or null*/, cudaStream_t stream);
+
+// argmax over candidates, EOS/pad bookkeeping, head switch, next-token embedding dispatch, pos++.
+int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, int B, int vocab, int eos, int pad,
+                    const __half* embed, const __half* time_tab, const __half* score_tab, const __half* sync_tab,
+                    int H, const DecodeState& st, __half* x_next, int advance_pos, cudaStream_t stream);
+
+}  // namespace tb

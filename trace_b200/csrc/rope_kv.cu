@@ -1,0 +1,63 @@
+// Prefill RoPE + paged KV-cache write (HF MistralAttention: apply_rotary_pos_emb on q,k; DynamicCache.update).
+// Operates in place on the fused qkv activation [B*S, (heads + 2*kvh) * hd] produced by the QKV GEMM:
+// q and k columns are rotated (rotate_half pairs d, d+hd/2; cos/sin tables hold the fp16-rounded values the
+// reference casts to, [max_pos, hd/2]); rotated k and raw v rows are appended to the page pool
+//   K/V pool layout: [page][kv_head][page_size][hd] fp16, page = block_table[slot][pos / page_size].
+// One CTA per token; HBM-bound: reads+writes the qkv row once, writes 2*kvh*hd halves to the pool.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tb {
+namespace {
+
+__global__ void __launch_bounds__(128)
+rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, const float* __restrict__ cos_tab,
+               const float* __restrict__ sin_tab, __half* __restrict__ k_pool, __half* __restrict__ v_pool,
+               const int32_t* __restrict__ block_table, const int32_t* __restrict__ slot_ids, int max_pages,
+               int page_size) {
+  const int tok = blockIdx.x;              // b*S + pos
+  const int b = tok / S, pos = tok % S;
+  const int hh = hd / 2;
+  __half* row = qkv + static_cast<int64_t>(tok) * (heads + 2 * kvh) * hd;
+  const int slot = slot_ids[b];
+  const int page = block_table[static_cast<int64_t>(slot) * max_pages + pos / page_size];
+  const int poff = pos % page_size;
+  // q and k heads: (heads + kvh) * hd/2 rotation pairs
+  const int npairs = (heads + kvh) * hh;
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
+    const int h = i / hh, d = i % hh;
+    __half* p = row + h * hd;
+    const float a = __half2float(p[d]), c2 = __half2float(p[d + hh]);
+    const float c = cos_tab[static_cast<int64_t>(pos) * hh + d], s = sin_tab[static_cast<int64_t>(pos) * hh + d];
+    const __half ra = __float2half_rn(a * c - c2 * s);
+    const __half rb = __float2half_rn(c2 * c + a * s);
+    p[d] = ra;
+    p[d + hh] = rb;
+    if (h >= heads) {
+      __half* kd = k_pool + ((static_cast<int64_t>(page) * kvh + (h - heads)) * page_size + poff) * hd;
+      kd[d] = ra;
+      kd[d + hh] = rb;
+    }
+  }
+  const __half* vsrc = row + (heads + kvh) * hd;
+  for (int i = threadIdx.x; i < kvh * hd / 8; i += blockDim.x) {
+    const int h = (i * 8) / hd, d = (i * 8) % hd;
+    __half* vd = v_pool + ((static_cast<int64_t>(page) * kvh + h) * page_size + poff) * hd + d;
+    *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vsrc + i * 8);
+  }
+}
+
+}  // namespace
+
+int rope_kv_prefill(__half* qkv, int B, int S, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
+                    __half* k_pool, __half* v_pool, const int32_t* block_table, const int32_t* slot_ids, int max_pages,
+                    int page_size, cudaStream_t stream) {
+  TB_CHECK(hd % 8 == 0, "head_dim must be a multiple of 8");
+  if (B * S == 0) return 0;
+  rope_kv_kernel<<<B * S, 128, 0, stream>>>(qkv, S, heads, kvh, hd, cos_tab, sin_tab, k_pool, v_pool, block_table,
+                                            slot_ids, max_pages, page_size);
+  TB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace tb
