@@ -97,6 +97,8 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
 /* Introspection used by bench.py: kernels launched by this context since creation, and bytes of weights. */
 int64_t trace_b200_launch_count(trace_b200_ctx* ctx);
 int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);
+/* device time (CUDA events on the engine's decode stream) and decoder passes of the last trace_b200_decode */
+int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps_out);
 
 /* ---- single-kernel entry points (unit-parity tests and micro-benchmarks) --------------------------- */
 int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,

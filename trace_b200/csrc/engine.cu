@@ -81,6 +81,11 @@ struct trace_b200_ctx {
   std::vector<bool> slot_used;
   // decode graphs keyed by batch
   std::map<int, cudaGraphExec_t> graphs;
+  // decode runs on an engine-owned stream (graph capture is illegal on the legacy default stream)
+  cudaStream_t dstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  float last_decode_ms = 0.f;
+  int last_decode_steps = 0;
 };
 
 namespace {
@@ -450,6 +455,10 @@ int trace_b200_create(const trace_b200_config* cfg, int device, trace_b200_ctx**
     trace_b200_destroy(ctx);
     return 1;
   }
+  TB_CUDA(cudaStreamCreateWithFlags(&ctx->dstream, cudaStreamNonBlocking));
+  TB_CUDA(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+  TB_CUDA(cudaEventCreate(&ctx->ev_t0));
+  TB_CUDA(cudaEventCreate(&ctx->ev_t1));
   *out = ctx;
   return 0;
 }
@@ -458,6 +467,10 @@ void trace_b200_destroy(trace_b200_ctx* ctx) {
   if (ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  if (ctx->dstream) cudaStreamDestroy(ctx->dstream);
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   for (void* p : ctx->allocs) cudaFree(p);
   delete ctx;
 }
@@ -573,7 +586,10 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   TB_CHECK(slots_host && heads_inout_host && ids_out_host && n_out && B >= 1 && B <= kMaxB && max_new >= 1, "bad arguments");
   const trace_b200_config& c = ctx->c;
   TB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // everything below runs on the engine's stream, ordered after the caller's stream (prefill was enqueued there)
+  TB_CUDA(cudaEventRecord(ctx->ev_in, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = ctx->dstream;
+  TB_CUDA(cudaStreamWaitEvent(s, ctx->ev_in, 0));
   std::vector<int32_t> pos(B), zeros(kMaxB, 0);
   for (int b = 0; b < B; ++b) {
     const int sl = slots_host[b];
@@ -593,6 +609,7 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   TB_CUDA(cudaMemcpyAsync(ctx->st.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
   const size_t lstride = static_cast<size_t>(B) * ctx->total_vocab;
 
+  TB_CUDA(cudaEventRecord(ctx->ev_t0, s));
   // token 0: heads on the prefill's last hidden state, no decoder pass, positions do not advance
   RUN(head_gemv(ctx->head_w, ctx->d_x, c.hidden, B, ctx->total_vocab, ctx->head_rows, c.hidden, ctx->final_norm, c.rms_eps, c.vocab,
                 ctx->st, ctx->d_cand_val, ctx->d_cand_idx, logits_out_dev, s));
@@ -643,7 +660,10 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
       if (done) break;
     }
   }
+  TB_CUDA(cudaEventRecord(ctx->ev_t1, s));
   if (poll_done()) return 1;
+  TB_CUDA(cudaEventElapsedTime(&ctx->last_decode_ms, ctx->ev_t0, ctx->ev_t1));
+  ctx->last_decode_steps = steps_run;
   const int n = done ? done : (steps_run < max_new ? steps_run : max_new);
   std::vector<int64_t> tmp(static_cast<size_t>(B) * max_new);
   TB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->st.out_ids, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
@@ -658,6 +678,12 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
 }
 
 int64_t trace_b200_launch_count(trace_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps_out) {
+  TB_CHECK(ctx != nullptr && ms_out != nullptr && steps_out != nullptr, "null argument");
+  *ms_out = ctx->last_decode_ms;
+  *steps_out = ctx->last_decode_steps;
+  return 0;
+}
 int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx) { return ctx ? ctx->weight_bytes : 0; }
 
 // ---- single-kernel entry points -----------------------------------------------------------------

@@ -21,7 +21,7 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_launch_count", "trace_b200_weight_bytes", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_op_gemm",
     "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_gemv",
 ]
 
@@ -68,6 +68,7 @@ def load_library() -> ctypes.CDLL:
                                       i32, ctypes.POINTER(i64), ctypes.POINTER(i32), vp, vp]
     lib.trace_b200_launch_count.argtypes = [vp]
     lib.trace_b200_launch_count.restype = i64
+    lib.trace_b200_last_decode_timing.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
     lib.trace_b200_weight_bytes.argtypes = [vp]
     lib.trace_b200_weight_bytes.restype = i64
     lib.trace_b200_op_gemm.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp]
@@ -209,6 +210,12 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.trace_b200_launch_count(self._h))
+
+    def last_decode_timing(self):
+        """(milliseconds on the device, decoder passes) of the most recent decode() call."""
+        ms, st = ctypes.c_float(0), ctypes.c_int(0)
+        _check(self.lib.trace_b200_last_decode_timing(self._h, ctypes.byref(ms), ctypes.byref(st)))
+        return ms.value, st.value
 
     @property
     def weight_bytes(self) -> int:

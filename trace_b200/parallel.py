@@ -1,0 +1,38 @@
+"""Multi-GPU: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+The only exchange step of the path: frames are independent through CLIP + projector, so every
+clip's T frames are split contiguously over the G ranks; each rank encodes its B*T/G frames and ONE
+all-gather of the projected slot tokens ([B, T/G, 8, hidden] fp16 per rank = 1 MiB per clip per rank at
+T/G=16) gives every rank the full [B, T, 8, hidden].  Gathering after the projector moves 18x fewer bytes than
+gathering CLIP features.  The LLM (prefill + decode) is replicated; rank r decodes clips r, r+G, ...
+No collective inside the decode loop."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def attach_group(model, group=None):
+    """Make `model.generate` shard its ViT encode over `group` (default: the world group)."""
+    model.dist_group = group if group is not None else dist.group.WORLD
+    return model
+
+
+def shard_bounds(T: int, world: int, rank: int):
+    """Contiguous frame range of `rank` (rank-major == frame-major so the gathered buffer is in t order)."""
+    assert T % world == 0, f"frames per clip ({T}) must divide evenly over {world} ranks"
+    per = T // world
+    return rank * per, (rank + 1) * per
+
+
+def encode_frames_sharded(engine, frames: torch.Tensor, B: int, T: int, group) -> torch.Tensor:
+    """frames [B*T,3,H,W] (every rank holds all clips) -> slots [B*T, 8, hidden] on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(T, world, rank)
+    fr = frames.view(B, T, *frames.shape[1:])[:, lo:hi].reshape(B * (hi - lo), *frames.shape[1:]).contiguous()
+    local = engine.encode_frames(fr)                                   # [B*(T/G), 8, H]
+    local = local.view(B, hi - lo, local.shape[1], local.shape[2])
+    gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    # [G, B, T/G, 8, H] -> [B, G, T/G, 8, H] -> [B*T, 8, H]
+    return gathered.permute(1, 0, 2, 3, 4).reshape(B * T, local.shape[2], local.shape[3]).contiguous()
