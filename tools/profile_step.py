@@ -1,0 +1,39 @@
+"""Run one generate() of the bench workload (for ncu launch lists / --set full captures).
+    python tools/profile_step.py --frames 128 --max-new 4 [--warm 1]
+Weights are random-synthetic (grammar irrelevant for profiling)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from bench import L_TEXT, bench_prompt_ids  # noqa: E402
+from trace_b200 import synth  # noqa: E402
+from trace_b200.model import TraceMistralConfig, TraceMistralForCausalLM  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=128)
+ap.add_argument("--max-new", type=int, default=4)
+ap.add_argument("--warm", type=int, default=0)
+ap.add_argument("--batch", type=int, default=1)
+a = ap.parse_args()
+d = synth.full_dims(a.frames)
+S = 14 * a.frames + L_TEXT - 1
+model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frames=32, max_prefill_tokens=S * a.batch,
+                                max_ctx=S + a.max_new + 64, kv_pages=(a.batch + 1) * ((S + a.max_new + 127) // 64))
+for name, shape, kind in synth.param_specs(d):
+    model.engine.load_weight(name, synth.synth_tensor(name, shape, kind, 0, device="cuda"))
+model.engine.load_state_dict([])
+ids = torch.tensor([bench_prompt_ids(a.frames)] * a.batch, dtype=torch.int64, device="cuda")
+clips, stamps = [], []
+for b in range(a.batch):
+    px, ts = synth.synthetic_clip(d, a.frames, seed=1234 + b)
+    clips.append(px.cuda())
+    stamps.append(ts)
+for i in range(a.warm + 1):
+    torch.cuda.synchronize()
+    out = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=clips, modal_list=["video"] * a.batch,
+                         video_timestamps=stamps, heads=[1] * a.batch, do_sample=False, max_new_tokens=a.max_new, pad_token_id=2)
+torch.cuda.synchronize()
+print("ids", out.tolist(), "decode timing", model.engine.last_decode_timing())

@@ -23,11 +23,20 @@ namespace {
 
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = 8;
-constexpr int GV_ROWS = 16;
+constexpr int GV_TILE = 16;   // rows per MMA tile
 constexpr int GV_MAXB = 8;
-constexpr int XS_PAD = 32;   // halves; row pitch = KP*2 + 64 bytes -> conflict-free 16-byte fragment reads
+constexpr int GV_RING = 8;    // weight chunks (2 x LDG.128 each) kept in flight per thread
+constexpr int XS_PAD = 32;    // halves; row pitch = KP*2 + 64 bytes -> conflict-free 16-byte fragment reads
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// Balanced static partition: rows are dealt to the CTAs in units of 2 (SwiGLU pairs stay together), so every
+// CTA streams the same number of weight bytes (+-2 rows) whatever N is -- no wave quantisation.
+__device__ __forceinline__ void cta_rows(int N, int& r0, int& r1) {
+  const long long U = N / 2;
+  r0 = static_cast<int>(U * blockIdx.x / gridDim.x) * 2;
+  r1 = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * 2;
+}
 
 // ---- activation staging (+ optional RMSNorm) into shared memory: xs[b][k], b < B, k in [k0, k0+KP) ----
 template <int PRO>
@@ -83,96 +92,155 @@ __device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, in
   }
 }
 
-// ---- main loop over one staged phase: 16 rows x KP columns, K split over the 8 warps ----
-__device__ __forceinline__ void gemv_phase(float (&c)[4], const __half* __restrict__ W, int K, int row0, int k0,
-                                           int KP, const __half* xs, int B) {
+// ---- the weight stream of one thread: items = (tile, 32-column chunk) in tile-major order -------------------
+// Each item is two 16-byte loads (rows g and g+8 of the tile).  Rows outside [vlo, vhi) are not loaded at all.
+struct WStream {
+  const __half* pa;     // row g of the current tile, this warp's K slice, this lane's 8 columns
+  int row;              // absolute row of slot g
+  int chunk, nch;       // chunk within the K slice
+  int vlo, vhi;         // valid row range
+  size_t tile_step;     // 16*K - nch*32
+  size_t K8;            // 8*K
+  __device__ __forceinline__ void load(uint4& a, uint4& b) {
+    a = (row >= vlo && row < vhi) ? ldg_nc_v4(pa) : make_uint4(0, 0, 0, 0);
+    b = (row + 8 >= vlo && row + 8 < vhi) ? ldg_nc_v4(pa + K8) : make_uint4(0, 0, 0, 0);
+    pa += 32;
+    if (++chunk == nch) { chunk = 0; pa += tile_step; row += GV_TILE; }
+  }
+};
+
+// Streams this CTA's rows [r0, r1) x columns [k0, k0+KP): K split over the 8 warps, GV_RING chunks in flight per
+// thread; per-tile partial sums are accumulated into s_part[tile][warp][16 rows][8 batch].
+// `preloaded` : the first ring was already issued (before griddepcontrol.wait) by the caller.
+__device__ __forceinline__ void gemv_stream(const __half* __restrict__ W, int K, int r0, int r1, int vlo, int vhi, int k0,
+                                            int KP, const __half* xs, int B, float* s_part, bool accumulate,
+                                            uint4 (&wa)[GV_RING], uint4 (&wb)[GV_RING], WStream& ld, bool preloaded) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wk = KP / GV_WARPS;                 // columns per warp (multiple of 32)
+  const int wk = KP / GV_WARPS;
   const int nch = wk / 32;
-  const __half* ra = W + static_cast<size_t>(row0 + g) * K + k0 + warp * wk + t * 8;
-  const __half* rb = ra + static_cast<size_t>(8) * K;
+  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
+  const int total = ntile * nch;
+  if (!preloaded) {
+    ld.pa = W + static_cast<size_t>(r0 + g) * K + k0 + warp * wk + t * 8;
+    ld.row = r0 + g; ld.chunk = 0; ld.nch = nch; ld.vlo = vlo; ld.vhi = vhi;
+    ld.tile_step = static_cast<size_t>(GV_TILE) * K - static_cast<size_t>(nch) * 32; ld.K8 = static_cast<size_t>(8) * K;
+#pragma unroll
+    for (int j = 0; j < GV_RING; ++j)
+      if (j < total) ld.load(wa[j], wb[j]);
+  }
   const __half* xp = xs + g * (KP + XS_PAD) + warp * wk + t * 8;
   const bool xok = g < B;
-  int ch = 0;
-  for (; ch + 4 <= nch; ch += 4) {
-    uint4 wa[4], wb[4], xv[4];
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  int cchunk = 0, ctile = 0;
+  float* pw = s_part + warp * (GV_TILE * 8);
+  for (int base = 0; base < total; base += GV_RING) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      wa[i] = ldg_nc_v4(ra + (ch + i) * 32);
-      wb[i] = ldg_nc_v4(rb + (ch + i) * 32);
+    for (int j = 0; j < GV_RING; ++j) {
+      if (base + j < total) {
+        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + cchunk * 32) : make_uint4(0, 0, 0, 0);
+        mma_16816(c, wa[j].x, wb[j].x, wa[j].y, wb[j].y, xv.x, xv.y);
+        mma_16816(c, wa[j].z, wb[j].z, wa[j].w, wb[j].w, xv.z, xv.w);
+        if (base + j + GV_RING < total) ld.load(wa[j], wb[j]);
+        if (++cchunk == nch) {                      // tile finished for this warp: flush its partial sums
+          float* p = pw + ctile * (GV_WARPS * GV_TILE * 8);
+          if (accumulate) {
+            p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
+            p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
+          } else {
+            p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
+            p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+          }
+          c[0] = c[1] = c[2] = c[3] = 0.f;
+          cchunk = 0;
+          ++ctile;
+        }
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xv[i] = xok ? *reinterpret_cast<const uint4*>(xp + (ch + i) * 32) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      mma_16816(c, wa[i].x, wb[i].x, wa[i].y, wb[i].y, xv[i].x, xv[i].y);
-      mma_16816(c, wa[i].z, wb[i].z, wa[i].w, wb[i].w, xv[i].z, xv[i].w);
-    }
-  }
-  for (; ch < nch; ++ch) {
-    uint4 wa = ldg_nc_v4(ra + ch * 32), wb = ldg_nc_v4(rb + ch * 32);
-    uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
-    mma_16816(c, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
-    mma_16816(c, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
   }
 }
 
-// cross-warp reduction; returns the value for (row = tid>>3, n = tid&7), valid for tid < 128
-__device__ __forceinline__ float gemv_reduce(const float (&c)[4], float* s_part) {
+// issue the first ring of weight loads (no dependence on the previous kernel's output)
+__device__ __forceinline__ void gemv_preload(const __half* __restrict__ W, int K, int r0, int r1, int vlo, int vhi, int k0,
+                                             int KP, uint4 (&wa)[GV_RING], uint4 (&wb)[GV_RING], WStream& ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  float* p = s_part + warp * (GV_ROWS * 8);
-  p[g * 8 + 2 * t] = c[0];
-  p[g * 8 + 2 * t + 1] = c[1];
-  p[(g + 8) * 8 + 2 * t] = c[2];
-  p[(g + 8) * 8 + 2 * t + 1] = c[3];
-  __syncthreads();
-  float v = 0.f;
-  if (threadIdx.x < 128) {
+  const int wk = KP / GV_WARPS;
+  const int nch = wk / 32;
+  const int total = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * nch;
+  ld.pa = W + static_cast<size_t>(r0 + g) * K + k0 + warp * wk + t * 8;
+  ld.row = r0 + g; ld.chunk = 0; ld.nch = nch; ld.vlo = vlo; ld.vhi = vhi;
+  ld.tile_step = static_cast<size_t>(GV_TILE) * K - static_cast<size_t>(nch) * 32; ld.K8 = static_cast<size_t>(8) * K;
 #pragma unroll
-    for (int w = 0; w < GV_WARPS; ++w) v += s_part[w * (GV_ROWS * 8) + threadIdx.x];
-  }
+  for (int j = 0; j < GV_RING; ++j)
+    if (j < total) ld.load(wa[j], wb[j]);
+}
+
+// sum of the 8 warps' partials for output `idx` = tile*128 + row*8 + n
+__device__ __forceinline__ float gemv_out(const float* s_part, int idx) {
+  const int tile = idx >> 7, rn = idx & 127;
+  const float* p = s_part + tile * (GV_WARPS * GV_TILE * 8) + rn;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < GV_WARPS; ++w) v += p[w * (GV_TILE * 8)];
   return v;
 }
 
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(GV_THREADS)
+__global__ void __launch_bounds__(GV_THREADS, 2)
 gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, __half* __restrict__ out, int ldo,
             int B, int N, int K, int KP, const __half* __restrict__ gamma, float eps) {
   extern __shared__ __align__(16) uint8_t smem[];
   __half* xs = reinterpret_cast<__half*>(smem);
-  float* s_part = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (KP + XS_PAD) * 2);
-  float* s_red = s_part + GV_WARPS * GV_ROWS * 8;
-  const int row0 = blockIdx.x * GV_ROWS;
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  float* s_red = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (KP + XS_PAD) * 2);
+  float* s_part = s_red + (GV_WARPS * GV_MAXB + GV_MAXB);
+  int r0, r1;
+  cta_rows(N, r0, r1);
+  pdl_launch_dependents();
+  uint4 wa[GV_RING], wb[GV_RING];
+  WStream ld;
+  gemv_preload(W, K, r0, r1, r0, r1, 0, KP, wa, wb, ld);   // weights never depend on the previous kernel
+  pdl_wait();                                              // activations do
   for (int k0 = 0; k0 < K; k0 += KP) {
     if (k0 > 0) __syncthreads();
     stage_x<PRO>(xs, x, ldx, B, k0, KP, K, gamma, eps, s_red);
     __syncthreads();
-    gemv_phase(c, W, K, row0, k0, KP, xs, B);
+    gemv_stream(W, K, r0, r1, r0, r1, k0, KP, xs, B, s_part, k0 > 0, wa, wb, ld, k0 == 0);
   }
-  const float v = gemv_reduce(c, s_part);
-  const int row = threadIdx.x >> 3, n = threadIdx.x & 7;
-  if (threadIdx.x < 128) {
+  __syncthreads();
+  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+  for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
+    const float v = gemv_out(s_part, idx);
+    const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
     if (EPI == 2) {
       const float partner = __shfl_xor_sync(0xffffffffu, v, 8);   // row ^ 1 (the `up` value for even rows)
-      if ((row & 1) == 0 && n < B) out[static_cast<size_t>(n) * ldo + ((row0 + row) >> 1)] = __float2half_rn(silu_f(v) * partner);
-    } else if (n < B) {
-      __half* o = out + static_cast<size_t>(n) * ldo + row0 + row;
+      if ((row & 1) == 0 && n < B && row < r1) out[static_cast<size_t>(n) * ldo + (row >> 1)] = __float2half_rn(silu_f(v) * partner);
+    } else if (n < B && row < r1) {
+      __half* o = out + static_cast<size_t>(n) * ldo + row;
       *o = (EPI == 1) ? __float2half_rn(v + __half2float(*o)) : __float2half_rn(v);
     }
   }
 }
 
-int pick_kp(int K) {
-  // largest multiple of 256 that divides K and is <= 4096
-  for (int kp = 4096; kp >= 256; kp -= 256)
-    if (K % kp == 0) return kp;
+int pick_kp(int K, int B) {
+  // largest multiple of 256 that divides K with the staged activations (B rows) <= 64 KB
+  for (int kp = 16384; kp >= 256; kp -= 256)
+    if (K % kp == 0 && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= 64 * 1024) return kp;
   return 0;
 }
 
-size_t gemv_smem(int KP, int B) { return static_cast<size_t>(B) * (KP + XS_PAD) * 2 + (GV_WARPS * GV_ROWS * 8 + GV_WARPS * GV_MAXB + GV_MAXB) * 4; }
+int gemv_grid(int N, int num_sms, int ctas_per_sm) {
+  int g = num_sms * ctas_per_sm;
+  if (g > N / 2) g = N / 2;
+  return g < 1 ? 1 : g;
+}
+
+size_t gemv_smem(int KP, int B, int N, int grid) {
+  const int rows = ((N / 2 + grid - 1) / grid) * 2 + 2;
+  const int tiles = (rows + GV_TILE - 1) / GV_TILE;
+  return static_cast<size_t>(B) * (KP + XS_PAD) * 2 + (GV_WARPS * GV_MAXB + GV_MAXB) * 4 +
+         static_cast<size_t>(tiles) * GV_WARPS * GV_TILE * 8 * 4;
+}
 
 template <typename Kern>
 int ensure_smem(Kern k, size_t bytes, size_t* cached) {
@@ -180,6 +248,24 @@ int ensure_smem(Kern k, size_t bytes, size_t* cached) {
     TB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
     *cached = bytes;
   }
+  return 0;
+}
+
+// launch with programmatic dependent launch enabled (the kernel calls griddepcontrol.wait before it touches
+// anything the previous kernel wrote)
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
   return 0;
 }
 
@@ -192,76 +278,81 @@ __device__ __forceinline__ void head_range(int h, int vocab, int& lo, int& hi) {
   else { lo = vocab + 14; hi = vocab + 27; }              // score head
 }
 
-__global__ void __launch_bounds__(GV_THREADS)
-head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, int B, int n_valid, int K,
+__global__ void __launch_bounds__(GV_THREADS, 2)
+head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, int B, int n_valid, int Npad, int K,
                  const __half* __restrict__ gamma, float eps, int vocab, const int32_t* __restrict__ heads,
                  float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, float* __restrict__ logits_out) {
   extern __shared__ __align__(16) uint8_t smem[];
   __half* xs = reinterpret_cast<__half*>(smem);
-  float* s_part = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (K + XS_PAD) * 2);
-  float* s_red = s_part + GV_WARPS * GV_ROWS * 8;
-  __shared__ float s_cv[4][8];
-  __shared__ int s_ci[4][8];
-  const int row0 = blockIdx.x * GV_ROWS;
+  float* s_red = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (K + XS_PAD) * 2);
+  float* s_part = s_red + (GV_WARPS * GV_MAXB + GV_MAXB);
+  __shared__ float s_cv[GV_WARPS][8];
+  __shared__ int s_ci[GV_WARPS][8];
+  int r0, r1;
+  cta_rows(Npad, r0, r1);
   const int ncta = gridDim.x;
+  pdl_launch_dependents();
+  pdl_wait();                                  // heads[] is written by the previous step's finalize kernel
   int lo[GV_MAXB], hi[GV_MAXB];
-  bool needed = false;
+  int ulo = 0x7fffffff, uhi = 0;
 #pragma unroll
   for (int b = 0; b < GV_MAXB; ++b) {
     lo[b] = hi[b] = 0;
     if (b < B) {
       head_range(heads[b], vocab, lo[b], hi[b]);
-      needed = needed || (row0 < hi[b] && row0 + GV_ROWS > lo[b]);
+      ulo = min(ulo, lo[b]);
+      uhi = max(uhi, hi[b]);
     }
   }
-  if (!needed) {   // no row decodes from this slice of the vocabulary at this step: skip the weight read
-    if (threadIdx.x < B) {
-      cand_val[threadIdx.x * ncta + blockIdx.x] = -INFINITY;
-      cand_idx[threadIdx.x * ncta + blockIdx.x] = 0x7fffffff;
-    }
-    if (logits_out != nullptr && threadIdx.x < 128) {
-      const int row = threadIdx.x >> 3, n = threadIdx.x & 7;
-      if (n < B && row0 + row < n_valid) logits_out[static_cast<size_t>(n) * n_valid + row0 + row] = -INFINITY;
-    }
-    return;
-  }
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
-  stage_x<1>(xs, x, ldx, B, 0, K, K, gamma, eps, s_red);
-  __syncthreads();
-  gemv_phase(c, W, K, row0, 0, K, xs, B);
-  float v = gemv_reduce(c, s_part);
-  const int row = threadIdx.x >> 3, n = threadIdx.x & 7;
-  int idx = 0x7fffffff;
-  if (threadIdx.x < 128) {
-    const int r = row0 + row;
-    v = __half2float(__float2half_rn(v));          // Linear output is fp16, then .float() (trace_mistral.py:191-200)
+  const int vlo = max(ulo, r0), vhi = min(uhi, r1);   // only rows some batch row decodes from are read at all
+  const int n = threadIdx.x & 7;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+  if (vlo < vhi) {
+    uint4 wa[GV_RING], wb[GV_RING];
+    WStream ld;
+    stage_x<1>(xs, x, ldx, B, 0, K, K, gamma, eps, s_red);
+    __syncthreads();
+    gemv_stream(W, K, r0, r1, vlo, vhi, 0, K, xs, B, s_part, false, wa, wb, ld, false);
+    __syncthreads();
     int l = 0, h = 0;
 #pragma unroll
     for (int b = 0; b < GV_MAXB; ++b) if (b == n) { l = lo[b]; h = hi[b]; }
-    if (n >= B || r < l || r >= h) v = -INFINITY;  // masked_fill of inactive ranges (:244-252)
-    else idx = r;
-    if (logits_out != nullptr && n < B && r < n_valid) logits_out[static_cast<size_t>(n) * n_valid + r] = v;
-    // argmax over the rows held by this warp (lanes n, n+8, n+16, n+24), first index on ties
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
+      const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+      float v = __half2float(__float2half_rn(gemv_out(s_part, idx)));   // Linear output is fp16, then .float() (trace_mistral.py:191-200)
+      const bool act = (n < B) && r < r1 && r >= l && r < h;             // masked_fill of inactive ranges (:244-252)
+      if (!act) v = -INFINITY;
+      if (logits_out != nullptr && n < B && r < r1 && r < n_valid) logits_out[static_cast<size_t>(n) * n_valid + r] = v;
+      if (act && (v > bv || (v == bv && r < bi))) { bv = v; bi = r; }
     }
-    if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = v; s_ci[threadIdx.x >> 5][n] = idx; }
+  } else if (logits_out != nullptr) {
+    for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
+      const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+      if (n < B && r < r1 && r < n_valid) logits_out[static_cast<size_t>(n) * n_valid + r] = -INFINITY;
+    }
   }
+  // argmax per batch row over the CTA: lanes with equal n (xor 8, 16), then the 8 warps; first index on ties
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
   __syncthreads();
   if (threadIdx.x < B) {
-    float bv = s_cv[0][threadIdx.x];
-    int bi = s_ci[0][threadIdx.x];
+    float v = s_cv[0][threadIdx.x];
+    int i = s_ci[0][threadIdx.x];
 #pragma unroll
-    for (int w = 1; w < 4; ++w) {
+    for (int w = 1; w < GV_WARPS; ++w) {
       const float ov = s_cv[w][threadIdx.x];
       const int oi = s_ci[w][threadIdx.x];
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
-    cand_val[threadIdx.x * ncta + blockIdx.x] = bv;
-    cand_idx[threadIdx.x * ncta + blockIdx.x] = bi;
+    cand_val[threadIdx.x * ncta + blockIdx.x] = v;
+    cand_idx[threadIdx.x * ncta + blockIdx.x] = i;
   }
 }
 
@@ -277,6 +368,8 @@ finalize_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ 
   __shared__ int s_i[8];
   __shared__ int s_tok[GV_MAXB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = *st.step;
   for (int b = 0; b < B; ++b) {
     float bv = -INFINITY;
@@ -352,6 +445,8 @@ attn_decode_kernel(const __half* __restrict__ qkv, int heads, int kvh, const flo
   __shared__ int s_last;
   const int split = blockIdx.x, kv = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = st.pos[b];                                 // cached keys; also the position id of the new token
   const int slot = st.slot_ids[b];
   const int32_t* table = block_table + static_cast<size_t>(slot) * max_pages;
@@ -400,28 +495,34 @@ attn_decode_kernel(const __half* __restrict__ qkv, int heads, int kvh, const flo
   const int end = min(start + chunk, t);
   const int nloc = max(end - start, 0);
 
-  // ---- phase A: scores, lane <-> key ----
-  for (int base = warp * 32; base < nloc; base += AD_THREADS) {
-    const int j = base + lane;
+  // ---- phase A: scores.  Two lanes per key (64 dims each), 16 keys per warp per pass; all 8 loads of a lane
+  //      are issued before the first FMA (memory-level parallelism: the KV rows come from HBM, not L2) ----
+  for (int base = warp * 16; base < nloc; base += 64) {
+    const int j = base + (lane >> 1);
+    const int hf = lane & 1;
     const bool valid = j < nloc;
     const int key = start + (valid ? j : 0);
     const int page = table[key / page_size];
-    const __half* kr = k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * AD_HD;
+    const __half* kr = k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * AD_HD + hf * 64;
+    uint4 kreg[8];
+#pragma unroll
+    for (int cI = 0; cI < 8; ++cI) kreg[cI] = *reinterpret_cast<const uint4*>(kr + cI * 8);
     float acc[AD_G] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int cI = 0; cI < AD_HD / 8; ++cI) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kr + cI * 8);
+#pragma unroll
+    for (int cI = 0; cI < 8; ++cI) {
       float kf[8];
-      float2 p0 = unpack_half2(u.x), p1 = unpack_half2(u.y), p2 = unpack_half2(u.z), p3 = unpack_half2(u.w);
+      float2 p0 = unpack_half2(kreg[cI].x), p1 = unpack_half2(kreg[cI].y), p2 = unpack_half2(kreg[cI].z), p3 = unpack_half2(kreg[cI].w);
       kf[0] = p0.x; kf[1] = p0.y; kf[2] = p1.x; kf[3] = p1.y; kf[4] = p2.x; kf[5] = p2.y; kf[6] = p3.x; kf[7] = p3.y;
 #pragma unroll
       for (int h = 0; h < AD_G; ++h) {
-        const float4 q0 = *reinterpret_cast<const float4*>(qs + h * AD_HD + cI * 8);
-        const float4 q1 = *reinterpret_cast<const float4*>(qs + h * AD_HD + cI * 8 + 4);
+        const float4 q0 = *reinterpret_cast<const float4*>(qs + h * AD_HD + hf * 64 + cI * 8);
+        const float4 q1 = *reinterpret_cast<const float4*>(qs + h * AD_HD + hf * 64 + cI * 8 + 4);
         acc[h] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
       }
     }
-    if (valid) {
+#pragma unroll
+    for (int h = 0; h < AD_G; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+    if (valid && hf == 0) {
 #pragma unroll
       for (int h = 0; h < AD_G; ++h) sc[h * cpitch + j] = acc[h];
     }
@@ -456,16 +557,26 @@ attn_decode_kernel(const __half* __restrict__ qkv, int heads, int kvh, const flo
   float o[AD_G][4];
 #pragma unroll
   for (int h = 0; h < AD_G; ++h) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
-  for (int j = warp; j < nloc; j += 4) {
-    const int key = start + j;
-    const int page = table[key / page_size];
-    const __half* vr = v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * AD_HD + lane * 4;
-    const uint2 u = *reinterpret_cast<const uint2*>(vr);
-    const float2 v0 = unpack_half2(u.x), v1 = unpack_half2(u.y);
+  for (int j0 = warp; j0 < nloc; j0 += 32) {       // 8 keys per pass per warp, loads first
+    uint2 vreg[8];
 #pragma unroll
-    for (int h = 0; h < AD_G; ++h) {
-      const float p = sc[h * cpitch + j];
-      o[h][0] += p * v0.x; o[h][1] += p * v0.y; o[h][2] += p * v1.x; o[h][3] += p * v1.y;
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * 4;
+      const int key = start + (j < nloc ? j : 0);
+      const int page = table[key / page_size];
+      vreg[u] = *reinterpret_cast<const uint2*>(v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * AD_HD + lane * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * 4;
+      if (j < nloc) {
+        const float2 v0 = unpack_half2(vreg[u].x), v1 = unpack_half2(vreg[u].y);
+#pragma unroll
+        for (int h = 0; h < AD_G; ++h) {
+          const float p = sc[h * cpitch + j];
+          o[h][0] += p * v0.x; o[h][1] += p * v0.y; o[h][2] += p * v1.x; o[h][3] += p * v1.y;
+        }
+      }
     }
   }
   if (split == 0 && warp == 0) {
@@ -528,21 +639,36 @@ attn_decode_kernel(const __half* __restrict__ qkv, int heads, int kvh, const flo
 
 }  // namespace
 
+static int g_num_sms = 0;
+static int g_ctas_per_sm = 1;
+static int gv_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+    const char* e = getenv("TRACE_B200_GEMV_CTAS_PER_SM");
+    if (e != nullptr && atoi(e) >= 1 && atoi(e) <= 2) g_ctas_per_sm = atoi(e);
+  }
+  return g_num_sms;
+}
+
 int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, int B, int N, int K, int pro,
              const __half* gamma, float eps, int epi, cudaStream_t stream) {
   TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
-  TB_CHECK(N % GV_ROWS == 0, "GEMV rows must be a multiple of 16");
-  const int KP = pick_kp(K);
+  TB_CHECK(N % 2 == 0 && N >= 2, "GEMV rows must be even");
+  const int KP = pick_kp(K, B);
   TB_CHECK(KP > 0, "GEMV K must be a multiple of 256");
-  TB_CHECK(!(pro == 1 && KP != K), "fused RMSNorm needs K <= 4096");
+  TB_CHECK(!(pro == 1 && KP != K), "fused RMSNorm needs the whole row staged (K <= 4096)");
   TB_CHECK(ldx % 8 == 0, "activation pitch must be 16-byte aligned");
-  const size_t smem = gemv_smem(KP, B);
-  const int grid = N / GV_ROWS;
-#define TB_GV(P, E)                                                                                   \
-  do {                                                                                                \
-    static size_t cached = 0;                                                                         \
-    if (ensure_smem(gemv_kernel<P, E>, smem, &cached)) return 1;                                      \
-    gemv_kernel<P, E><<<grid, GV_THREADS, smem, stream>>>(W, x, ldx, out, ldo, B, N, K, KP, gamma, eps); \
+  const int grid = gemv_grid(N, gv_sms(), g_ctas_per_sm);
+  const size_t smem = gemv_smem(KP, B, N, grid);
+  TB_CHECK(smem <= 220 * 1024, "GEMV shared memory budget exceeded");
+#define TB_GV(P, E)                                                                                              \
+  do {                                                                                                           \
+    static size_t cached = 0;                                                                                    \
+    if (ensure_smem(gemv_kernel<P, E>, smem, &cached)) return 1;                                                 \
+    if (launch_pdl(gemv_kernel<P, E>, dim3(grid), dim3(GV_THREADS), smem, stream, W, x, ldx, out, ldo, B, N, K, KP, gamma, eps)) return 1; \
   } while (0)
   if (pro == 0 && epi == 0) TB_GV(0, 0);
   else if (pro == 0 && epi == 1) TB_GV(0, 1);
@@ -552,9 +678,10 @@ int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, in
   else if (pro == 1 && epi == 1) TB_GV(1, 1);
   else TB_CHECK(false, "unsupported GEMV prologue/epilogue combination");
 #undef TB_GV
-  TB_LAUNCH_OK();
   return 0;
 }
+
+int head_gemv_ncand() { return gemv_grid(1 << 30, gv_sms(), g_ctas_per_sm); }
 
 int attn_decode(const __half* qkv, int B, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
                 __half* k_pool, __half* v_pool, const int32_t* block_table, int max_pages, int page_size,
@@ -567,34 +694,28 @@ int attn_decode(const __half* qkv, int B, int heads, int kvh, int hd, const floa
   TB_CHECK(smem <= 200 * 1024, "decode attention chunk does not fit shared memory; raise nsplit");
   static size_t cached = 0;
   if (ensure_smem(attn_decode_kernel, smem, &cached)) return 1;
-  attn_decode_kernel<<<dim3(nsplit, kvh, B), AD_THREADS, smem, stream>>>(qkv, heads, kvh, cos_tab, sin_tab, k_pool, v_pool,
-                                                                         block_table, max_pages, page_size, st, nsplit,
-                                                                         chunk_max, part_o, part_ml, counters, attn_out);
-  TB_LAUNCH_OK();
-  return 0;
+  return launch_pdl(attn_decode_kernel, dim3(nsplit, kvh, B), dim3(AD_THREADS), smem, stream, qkv, heads, kvh, cos_tab, sin_tab,
+                    k_pool, v_pool, block_table, max_pages, page_size, st, nsplit, chunk_max, part_o, part_ml, counters, attn_out);
 }
 
 int head_gemv(const __half* Wh, const __half* x, int ldx, int B, int n_valid, int Npad, int K, const __half* gamma,
               float eps, int vocab, const DecodeState& st, float* cand_val, int32_t* cand_idx, float* logits_out,
               cudaStream_t stream) {
   TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
-  TB_CHECK(Npad % GV_ROWS == 0 && K % 256 == 0 && K <= 4096, "head GEMV shape");
-  const size_t smem = gemv_smem(K, B);
+  TB_CHECK(Npad % 2 == 0 && K % 256 == 0 && K <= 4096, "head GEMV shape");
+  const int grid = head_gemv_ncand();
+  const size_t smem = gemv_smem(K, B, Npad, grid);
   static size_t cached = 0;
   if (ensure_smem(head_gemv_kernel, smem, &cached)) return 1;
-  head_gemv_kernel<<<Npad / GV_ROWS, GV_THREADS, smem, stream>>>(Wh, x, ldx, B, n_valid, K, gamma, eps, vocab, st.heads,
-                                                                 cand_val, cand_idx, logits_out);
-  TB_LAUNCH_OK();
-  return 0;
+  return launch_pdl(head_gemv_kernel, dim3(grid), dim3(GV_THREADS), smem, stream, Wh, x, ldx, B, n_valid, Npad, K, gamma, eps, vocab,
+                    static_cast<const int32_t*>(st.heads), cand_val, cand_idx, logits_out);
 }
 
 int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, int B, int vocab, int eos, int pad,
                     const __half* embed, const __half* time_tab, const __half* score_tab, const __half* sync_tab,
                     int H, const DecodeState& st, __half* x_next, int advance_pos, cudaStream_t stream) {
-  finalize_kernel<<<1, 256, 0, stream>>>(cand_val, cand_idx, ncand, B, vocab, eos, pad, embed, time_tab, score_tab,
-                                         sync_tab, H, st, x_next, advance_pos);
-  TB_LAUNCH_OK();
-  return 0;
+  return launch_pdl(finalize_kernel, dim3(1), dim3(256), 0, stream, cand_val, cand_idx, ncand, B, vocab, eos, pad, embed, time_tab,
+                    score_tab, sync_tab, H, st, x_next, advance_pos);
 }
 
 }  // namespace tb

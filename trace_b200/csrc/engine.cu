@@ -211,8 +211,8 @@ int allocate_all(trace_b200_ctx* ctx) {
       dalloc(ctx, &ctx->d_part_o, static_cast<size_t>(kMaxB) * c.kv_heads * 64 * 512) ||
       dalloc(ctx, &ctx->d_part_ml, static_cast<size_t>(kMaxB) * c.kv_heads * 64 * 8) ||
       dalloc(ctx, &ctx->d_counters, static_cast<size_t>(kMaxB) * c.kv_heads, true) ||
-      dalloc(ctx, &ctx->d_cand_val, static_cast<size_t>(kMaxB) * (ctx->head_rows / 16)) ||
-      dalloc(ctx, &ctx->d_cand_idx, static_cast<size_t>(kMaxB) * (ctx->head_rows / 16)))
+      dalloc(ctx, &ctx->d_cand_val, static_cast<size_t>(kMaxB) * 1024) ||
+      dalloc(ctx, &ctx->d_cand_idx, static_cast<size_t>(kMaxB) * 1024))
     return 1;
   if (dalloc(ctx, &ctx->st.pos, kMaxB, true) || dalloc(ctx, &ctx->st.heads, kMaxB, true) ||
       dalloc(ctx, &ctx->st.finished, kMaxB, true) || dalloc(ctx, &ctx->st.step, 1, true) ||
@@ -419,7 +419,7 @@ int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out,
   }
   RUN(head_gemv(ctx->head_w, ctx->d_x, H, B, ctx->total_vocab, ctx->head_rows, H, ctx->final_norm, c.rms_eps, c.vocab, ctx->st,
                 ctx->d_cand_val, ctx->d_cand_idx, logits_out, s));
-  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, ctx->head_rows / 16, B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
+  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, head_gemv_ncand(), B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
                       ctx->score_tab, ctx->sync_tab, H, ctx->st, ctx->d_x, 1, s));
   return 0;
 }
@@ -613,7 +613,7 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   // token 0: heads on the prefill's last hidden state, no decoder pass, positions do not advance
   RUN(head_gemv(ctx->head_w, ctx->d_x, c.hidden, B, ctx->total_vocab, ctx->head_rows, c.hidden, ctx->final_norm, c.rms_eps, c.vocab,
                 ctx->st, ctx->d_cand_val, ctx->d_cand_idx, logits_out_dev, s));
-  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, ctx->head_rows / 16, B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
+  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, head_gemv_ncand(), B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
                       ctx->score_tab, ctx->sync_tab, c.hidden, ctx->st, ctx->d_x, 0, s));
   int done = 0;
   int steps_run = 1;

@@ -78,6 +78,8 @@ int head_gemv(const __half* Wh, const __half* x, int ldx, int B, int n_valid, in
               float eps, int vocab, const DecodeState& st, float* cand_val, int32_t* cand_idx,
               float* logits_out /*[B, n_valid] or null*/, cudaStream_t stream);
 
+int head_gemv_ncand();   // candidates per batch row written by head_gemv (= its grid size)
+
 // argmax over candidates, EOS/pad bookkeeping, head switch, next-token embedding dispatch, pos++.
 int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, int B, int vocab, int eos, int pad,
                     const __half* embed, const __half* time_tab, const __half* score_tab, const __half* sync_tab,
