@@ -21,14 +21,17 @@
 namespace tb {
 namespace {
 
-constexpr int GV_THREADS = 256;
+constexpr int GV_CONS = 256;            // 8 consumer warps (MMA + epilogue)
+constexpr int GV_THREADS = GV_CONS + 32; // + 1 producer warp (TMA bulk copies)
 constexpr int GV_WARPS = 8;
-constexpr int GV_TILE = 16;   // rows per MMA tile
+constexpr int GV_TILE = 16;              // rows per MMA tile
 constexpr int GV_MAXB = 8;
-constexpr int GV_RING = 8;    // weight chunks (2 x LDG.128 each) kept in flight per thread
-constexpr int XS_PAD = 32;    // halves; row pitch = KP*2 + 64 bytes -> conflict-free 16-byte fragment reads
+constexpr int GV_MAXSTAGES = 8;
+constexpr int XS_PAD = 32;               // halves; row pitch = KP*2 + 64 bytes -> conflict-free 16-byte fragment reads
+constexpr int WS_PAD = 32;               // same trick for the weight stages
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // consumer warps only
 
 // Balanced static partition: rows are dealt to the CTAs in units of 2 (SwiGLU pairs stay together), so every
 // CTA streams the same number of weight bytes (+-2 rows) whatever N is -- no wave quantisation.
@@ -38,7 +41,13 @@ __device__ __forceinline__ void cta_rows(int N, int& r0, int& r1) {
   r1 = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * 2;
 }
 
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- activation staging (+ optional RMSNorm) into shared memory: xs[b][k], b < B, k in [k0, k0+KP) ----
+// executed by the 256 consumer threads only
 template <int PRO>
 __device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, int B, int k0, int KP, int K,
                                         const __half* gamma, float eps, float* s_red) {
@@ -51,7 +60,7 @@ __device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, in
     for (int b = 0; b < GV_MAXB; ++b) {
       ss[b] = 0.f;
       if (b < B) {
-        for (int i = tid; i < K / 8; i += GV_THREADS) {
+        for (int i = tid; i < K / 8; i += GV_CONS) {
           uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + i * 8);
           float2 a = unpack_half2(u.x), c = unpack_half2(u.y), d = unpack_half2(u.z), e = unpack_half2(u.w);
           ss[b] += a.x * a.x + a.y * a.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y + e.x * e.x + e.y * e.y;
@@ -63,17 +72,17 @@ __device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, in
     if (l == 0)
 #pragma unroll
       for (int b = 0; b < GV_MAXB; ++b) s_red[w * GV_MAXB + b] = ss[b];
-    __syncthreads();
+    cons_sync();
     if (tid < GV_MAXB) {
       float t = 0.f;
       for (int i = 0; i < GV_WARPS; ++i) t += s_red[i * GV_MAXB + tid];
       s_red[GV_WARPS * GV_MAXB + tid] = rsqrtf(t / K + eps);
     }
-    __syncthreads();
+    cons_sync();
   }
   for (int b = 0; b < B; ++b) {
     const float rstd = (PRO == 1) ? s_red[GV_WARPS * GV_MAXB + b] : 1.f;
-    for (int i = tid; i < KP / 8; i += GV_THREADS) {
+    for (int i = tid; i < KP / 8; i += GV_CONS) {
       uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8);
       if (PRO == 1) {
         uint4 gm = *reinterpret_cast<const uint4*>(gamma + k0 + i * 8);
@@ -92,88 +101,98 @@ __device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, in
   }
 }
 
-// ---- the weight stream of one thread: items = (tile, 32-column chunk) in tile-major order -------------------
-// Each item is two 16-byte loads (rows g and g+8 of the tile).  Rows outside [vlo, vhi) are not loaded at all.
-struct WStream {
-  const __half* pa;     // row g of the current tile, this warp's K slice, this lane's 8 columns
-  int row;              // absolute row of slot g
-  int chunk, nch;       // chunk within the K slice
-  int vlo, vhi;         // valid row range
-  size_t tile_step;     // 16*K - nch*32
-  size_t K8;            // 8*K
-  __device__ __forceinline__ void load(uint4& a, uint4& b) {
-    a = (row >= vlo && row < vhi) ? ldg_nc_v4(pa) : make_uint4(0, 0, 0, 0);
-    b = (row + 8 >= vlo && row + 8 < vhi) ? ldg_nc_v4(pa + K8) : make_uint4(0, 0, 0, 0);
-    pa += 32;
-    if (++chunk == nch) { chunk = 0; pa += tile_step; row += GV_TILE; }
-  }
+// Shared-memory carve-up of a GEMV CTA.
+struct GvSmem {
+  __half* xs;          // [B][KP + XS_PAD]
+  float* s_red;        // rmsnorm scratch
+  float* s_part;       // [tiles][8 warps][16 rows][8 batch]
+  uint64_t* full;      // [stages]
+  uint64_t* empty;     // [stages]
+  __half* ws;          // [stages][16][KS + WS_PAD]
 };
+__device__ __forceinline__ GvSmem gv_carve(uint8_t* smem, int B, int KP, int KS, int max_tiles, int stages) {
+  GvSmem m;
+  size_t off = 0;
+  m.ws = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(stages) * GV_TILE * (KS + WS_PAD) * 2;
+  m.xs = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(B) * (KP + XS_PAD) * 2;
+  m.s_part = reinterpret_cast<float*>(smem + off); off += static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
+  m.s_red = reinterpret_cast<float*>(smem + off); off += (GV_WARPS * GV_MAXB + GV_MAXB) * 4;
+  m.full = reinterpret_cast<uint64_t*>(smem + off); off += GV_MAXSTAGES * 8;
+  m.empty = reinterpret_cast<uint64_t*>(smem + off);
+  return m;
+}
 
-// Streams this CTA's rows [r0, r1) x columns [k0, k0+KP): K split over the 8 warps, GV_RING chunks in flight per
-// thread; per-tile partial sums are accumulated into s_part[tile][warp][16 rows][8 batch].
-// `preloaded` : the first ring was already issued (before griddepcontrol.wait) by the caller.
-__device__ __forceinline__ void gemv_stream(const __half* __restrict__ W, int K, int r0, int r1, int vlo, int vhi, int k0,
-                                            int KP, const __half* xs, int B, float* s_part, bool accumulate,
-                                            uint4 (&wa)[GV_RING], uint4 (&wb)[GV_RING], WStream& ld, bool preloaded) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int wk = KP / GV_WARPS;
-  const int nch = wk / 32;
+// ---- producer warp: streams rows [vlo,vhi) of the tiles of [r0,r1) in (phase, tile, k-stage) order ----------
+// One bulk copy per valid row per stage (lanes 0..15 issue them in one instruction); the copies do not depend on
+// the previous kernel, so this warp never executes griddepcontrol.wait and runs up to `stages` stages ahead.
+__device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
+                                              int vhi, const GvSmem& m, int stages) {
+  const int lane = threadIdx.x & 31;
   const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
-  const int total = ntile * nch;
-  if (!preloaded) {
-    ld.pa = W + static_cast<size_t>(r0 + g) * K + k0 + warp * wk + t * 8;
-    ld.row = r0 + g; ld.chunk = 0; ld.nch = nch; ld.vlo = vlo; ld.vhi = vhi;
-    ld.tile_step = static_cast<size_t>(GV_TILE) * K - static_cast<size_t>(nch) * 32; ld.K8 = static_cast<size_t>(8) * K;
-#pragma unroll
-    for (int j = 0; j < GV_RING; ++j)
-      if (j < total) ld.load(wa[j], wb[j]);
-  }
-  const __half* xp = xs + g * (KP + XS_PAD) + warp * wk + t * 8;
-  const bool xok = g < B;
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
-  int cchunk = 0, ctile = 0;
-  float* pw = s_part + warp * (GV_TILE * 8);
-  for (int base = 0; base < total; base += GV_RING) {
-#pragma unroll
-    for (int j = 0; j < GV_RING; ++j) {
-      if (base + j < total) {
-        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + cchunk * 32) : make_uint4(0, 0, 0, 0);
-        mma_16816(c, wa[j].x, wb[j].x, wa[j].y, wb[j].y, xv.x, xv.y);
-        mma_16816(c, wa[j].z, wb[j].z, wa[j].w, wb[j].w, xv.z, xv.w);
-        if (base + j + GV_RING < total) ld.load(wa[j], wb[j]);
-        if (++cchunk == nch) {                      // tile finished for this warp: flush its partial sums
-          float* p = pw + ctile * (GV_WARPS * GV_TILE * 8);
-          if (accumulate) {
-            p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
-            p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
-          } else {
-            p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
-            p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
-          }
-          c[0] = c[1] = c[2] = c[3] = 0.f;
-          cchunk = 0;
-          ++ctile;
-        }
+  const int pitch = KS + WS_PAD;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int k0 = 0; k0 < K; k0 += KP) {
+    for (int tile = 0; tile < ntile; ++tile) {
+      const int tr0 = r0 + tile * GV_TILE;
+      const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
+      if (lo >= hi) continue;                      // no row of this tile is needed (head GEMV on a narrow head)
+      for (int ks = 0; ks < KP; ks += KS) {
+        mbar_wait(&m.empty[s], ph ^ 1);
+        if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
+        __syncwarp();
+        const int row = tr0 + lane;
+        if (lane < GV_TILE && row >= lo && row < hi)
+          bulk_g2s(m.ws + (static_cast<size_t>(s) * GV_TILE + lane) * pitch, W + static_cast<size_t>(row) * K + k0 + ks, KS * 2, &m.full[s]);
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   }
 }
 
-// issue the first ring of weight loads (no dependence on the previous kernel's output)
-__device__ __forceinline__ void gemv_preload(const __half* __restrict__ W, int K, int r0, int r1, int vlo, int vhi, int k0,
-                                             int KP, uint4 (&wa)[GV_RING], uint4 (&wb)[GV_RING], WStream& ld) {
+// ---- consumer warps: MMA over the staged tiles; partial sums per (tile, warp) in shared memory ---------------
+__device__ __forceinline__ void gemv_consume_phase(int k0, int KP, int KS, int r0, int r1, int vlo, int vhi, const GvSmem& m,
+                                                   int B, int stages, int& s, uint32_t& ph) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wk = KP / GV_WARPS;
-  const int nch = wk / 32;
-  const int total = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * nch;
-  ld.pa = W + static_cast<size_t>(r0 + g) * K + k0 + warp * wk + t * 8;
-  ld.row = r0 + g; ld.chunk = 0; ld.nch = nch; ld.vlo = vlo; ld.vhi = vhi;
-  ld.tile_step = static_cast<size_t>(GV_TILE) * K - static_cast<size_t>(nch) * 32; ld.K8 = static_cast<size_t>(8) * K;
-#pragma unroll
-  for (int j = 0; j < GV_RING; ++j)
-    if (j < total) ld.load(wa[j], wb[j]);
+  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
+  const int ksw = KS / GV_WARPS;                  // columns of a stage owned by this warp (multiple of 32)
+  const int nch = ksw / 32;
+  const int wpitch = KS + WS_PAD;
+  const bool xok = g < B;
+  for (int tile = 0; tile < ntile; ++tile) {
+    const int tr0 = r0 + tile * GV_TILE;
+    float* p = m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * 8);
+    if (max(tr0, vlo) >= min(tr0 + GV_TILE, vhi)) {
+      if (k0 == 0) { p[g * 8 + 2 * t] = 0.f; p[g * 8 + 2 * t + 1] = 0.f; p[(g + 8) * 8 + 2 * t] = 0.f; p[(g + 8) * 8 + 2 * t + 1] = 0.f; }
+      continue;
+    }
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < KP; ks += KS) {
+      mbar_wait(&m.full[s], ph);
+      const __half* wa = m.ws + (static_cast<size_t>(s) * GV_TILE + g) * wpitch + warp * ksw + t * 8;
+      const __half* wb = wa + 8 * wpitch;
+      const __half* xp = m.xs + g * (KP + XS_PAD) + ks + warp * ksw + t * 8;
+#pragma unroll 4
+      for (int ch = 0; ch < nch; ++ch) {
+        const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+        const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
+        mma_16816(c, a.x, b.x, a.y, b.y, xv.x, xv.y);
+        mma_16816(c, a.z, b.z, a.w, b.w, xv.z, xv.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&m.empty[s]);
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+    if (k0 > 0) {
+      p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
+      p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
+    } else {
+      p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
+      p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+    }
+  }
 }
 
 // sum of the 8 warps' partials for output `idx` = tile*128 + row*8 + n
@@ -186,31 +205,44 @@ __device__ __forceinline__ float gemv_out(const float* s_part, int idx) {
   return v;
 }
 
-template <int PRO, int EPI>
-__global__ void __launch_bounds__(GV_THREADS, 2)
-gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, __half* __restrict__ out, int ldo,
-            int B, int N, int K, int KP, const __half* __restrict__ gamma, float eps) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __half* xs = reinterpret_cast<__half*>(smem);
-  float* s_red = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (KP + XS_PAD) * 2);
-  float* s_part = s_red + (GV_WARPS * GV_MAXB + GV_MAXB);
-  int r0, r1;
-  cta_rows(N, r0, r1);
-  pdl_launch_dependents();
-  uint4 wa[GV_RING], wb[GV_RING];
-  WStream ld;
-  gemv_preload(W, K, r0, r1, r0, r1, 0, KP, wa, wb, ld);   // weights never depend on the previous kernel
-  pdl_wait();                                              // activations do
-  for (int k0 = 0; k0 < K; k0 += KP) {
-    if (k0 > 0) __syncthreads();
-    stage_x<PRO>(xs, x, ldx, B, k0, KP, K, gamma, eps, s_red);
-    __syncthreads();
-    gemv_stream(W, K, r0, r1, r0, r1, k0, KP, xs, B, s_part, k0 > 0, wa, wb, ld, k0 == 0);
+__device__ __forceinline__ void gv_init_barriers(const GvSmem& m, int stages) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&m.full[i], 1);
+      mbar_init(&m.empty[i], GV_WARPS);
+    }
+    fence_barrier_init();
   }
   __syncthreads();
+}
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(GV_THREADS, 1)
+gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, __half* __restrict__ out, int ldo,
+            int B, int N, int K, int KP, int KS, int max_tiles, int stages, const __half* __restrict__ gamma, float eps) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const GvSmem m = gv_carve(smem, B, KP, KS, max_tiles, stages);
+  int r0, r1;
+  cta_rows(N, r0, r1);
+  gv_init_barriers(m, stages);
+  pdl_launch_dependents();
+  if (threadIdx.x >= GV_CONS) {
+    gemv_producer(W, K, KP, KS, r0, r1, r0, r1, m, stages);    // weights never depend on the previous kernel
+    return;
+  }
+  pdl_wait();                                                  // activations do
+  int s = 0;
+  uint32_t ph = 0;
+  for (int k0 = 0; k0 < K; k0 += KP) {
+    if (k0 > 0) cons_sync();
+    stage_x<PRO>(m.xs, x, ldx, B, k0, KP, K, gamma, eps, m.s_red);
+    cons_sync();
+    gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, B, stages, s, ph);
+  }
+  cons_sync();
   const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
-  for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
-    const float v = gemv_out(s_part, idx);
+  for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+    const float v = gemv_out(m.s_part, idx);
     const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
     if (EPI == 2) {
       const float partner = __shfl_xor_sync(0xffffffffu, v, 8);   // row ^ 1 (the `up` value for even rows)
@@ -228,18 +260,36 @@ int pick_kp(int K, int B) {
     if (K % kp == 0 && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= 64 * 1024) return kp;
   return 0;
 }
+int pick_ks(int KP) {
+  for (int ks = 1024; ks >= 256; ks -= 256)
+    if (KP % ks == 0) return ks;
+  return 0;
+}
 
-int gemv_grid(int N, int num_sms, int ctas_per_sm) {
-  int g = num_sms * ctas_per_sm;
+int gemv_grid(int N, int num_sms) {
+  int g = num_sms;
   if (g > N / 2) g = N / 2;
   return g < 1 ? 1 : g;
 }
 
-size_t gemv_smem(int KP, int B, int N, int grid) {
-  const int rows = ((N / 2 + grid - 1) / grid) * 2 + 2;
-  const int tiles = (rows + GV_TILE - 1) / GV_TILE;
-  return static_cast<size_t>(B) * (KP + XS_PAD) * 2 + (GV_WARPS * GV_MAXB + GV_MAXB) * 4 +
-         static_cast<size_t>(tiles) * GV_WARPS * GV_TILE * 8 * 4;
+struct GvPlan { int KP, KS, max_tiles, stages, grid; size_t smem; };
+int gemv_plan(int N, int K, int B, int kp_force, int num_sms, GvPlan* p) {
+  p->KP = kp_force > 0 ? kp_force : pick_kp(K, B);
+  TB_CHECK(p->KP > 0, "GEMV K must be a multiple of 256");
+  p->KS = pick_ks(p->KP);
+  p->grid = gemv_grid(N, num_sms);
+  const int rows = ((N / 2 + p->grid - 1) / p->grid) * 2 + 2;
+  p->max_tiles = (rows + GV_TILE - 1) / GV_TILE;
+  const size_t fixed = static_cast<size_t>(B) * (p->KP + XS_PAD) * 2 + static_cast<size_t>(p->max_tiles) * GV_WARPS * GV_TILE * 8 * 4 +
+                       (GV_WARPS * GV_MAXB + GV_MAXB) * 4 + 2 * GV_MAXSTAGES * 8 + 128;
+  const size_t stage = static_cast<size_t>(GV_TILE) * (p->KS + WS_PAD) * 2;
+  const size_t budget = 200 * 1024;
+  TB_CHECK(fixed + 2 * stage <= budget, "GEMV shared memory budget exceeded");
+  int st = static_cast<int>((budget - fixed) / stage);
+  if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;
+  p->stages = st;
+  p->smem = fixed + st * stage;
+  return 0;
 }
 
 template <typename Kern>
@@ -278,19 +328,19 @@ __device__ __forceinline__ void head_range(int h, int vocab, int& lo, int& hi) {
   else { lo = vocab + 14; hi = vocab + 27; }              // score head
 }
 
-__global__ void __launch_bounds__(GV_THREADS, 2)
+__global__ void __launch_bounds__(GV_THREADS, 1)
 head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, int B, int n_valid, int Npad, int K,
-                 const __half* __restrict__ gamma, float eps, int vocab, const int32_t* __restrict__ heads,
-                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, float* __restrict__ logits_out) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __half* xs = reinterpret_cast<__half*>(smem);
-  float* s_red = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * (K + XS_PAD) * 2);
-  float* s_part = s_red + (GV_WARPS * GV_MAXB + GV_MAXB);
+                 int KS, int max_tiles, int stages, const __half* __restrict__ gamma, float eps, int vocab,
+                 const int32_t* __restrict__ heads, float* __restrict__ cand_val, int32_t* __restrict__ cand_idx,
+                 float* __restrict__ logits_out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const GvSmem m = gv_carve(smem, B, K, KS, max_tiles, stages);
   __shared__ float s_cv[GV_WARPS][8];
   __shared__ int s_ci[GV_WARPS][8];
   int r0, r1;
   cta_rows(Npad, r0, r1);
   const int ncta = gridDim.x;
+  gv_init_barriers(m, stages);
   pdl_launch_dependents();
   pdl_wait();                                  // heads[] is written by the previous step's finalize kernel
   int lo[GV_MAXB], hi[GV_MAXB];
@@ -305,30 +355,34 @@ head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int
     }
   }
   const int vlo = max(ulo, r0), vhi = min(uhi, r1);   // only rows some batch row decodes from are read at all
+  if (threadIdx.x >= GV_CONS) {
+    if (vlo < vhi) gemv_producer(W, K, K, KS, r0, r1, vlo, vhi, m, stages);
+    return;
+  }
   const int n = threadIdx.x & 7;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
   if (vlo < vhi) {
-    uint4 wa[GV_RING], wb[GV_RING];
-    WStream ld;
-    stage_x<1>(xs, x, ldx, B, 0, K, K, gamma, eps, s_red);
-    __syncthreads();
-    gemv_stream(W, K, r0, r1, vlo, vhi, 0, K, xs, B, s_part, false, wa, wb, ld, false);
-    __syncthreads();
+    stage_x<1>(m.xs, x, ldx, B, 0, K, K, gamma, eps, m.s_red);
+    cons_sync();
+    int s = 0;
+    uint32_t ph = 0;
+    gemv_consume_phase(0, K, KS, r0, r1, vlo, vhi, m, B, stages, s, ph);
+    cons_sync();
     int l = 0, h = 0;
 #pragma unroll
     for (int b = 0; b < GV_MAXB; ++b) if (b == n) { l = lo[b]; h = hi[b]; }
-    for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
+    for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
       const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
-      float v = __half2float(__float2half_rn(gemv_out(s_part, idx)));   // Linear output is fp16, then .float() (trace_mistral.py:191-200)
-      const bool act = (n < B) && r < r1 && r >= l && r < h;             // masked_fill of inactive ranges (:244-252)
+      float v = __half2float(__float2half_rn(gemv_out(m.s_part, idx)));   // Linear output is fp16, then .float() (trace_mistral.py:191-200)
+      const bool act = (n < B) && r < r1 && r >= l && r < h;               // masked_fill of inactive ranges (:244-252)
       if (!act) v = -INFINITY;
       if (logits_out != nullptr && n < B && r < r1 && r < n_valid) logits_out[static_cast<size_t>(n) * n_valid + r] = v;
       if (act && (v > bv || (v == bv && r < bi))) { bv = v; bi = r; }
     }
   } else if (logits_out != nullptr) {
-    for (int idx = threadIdx.x; idx < nout; idx += GV_THREADS) {
+    for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
       const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
       if (n < B && r < r1 && r < n_valid) logits_out[static_cast<size_t>(n) * n_valid + r] = -INFINITY;
     }
@@ -341,7 +395,7 @@ head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
   if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
-  __syncthreads();
+  cons_sync();
   if (threadIdx.x < B) {
     float v = s_cv[0][threadIdx.x];
     int i = s_ci[0][threadIdx.x];
@@ -640,15 +694,12 @@ attn_decode_kernel(const __half* __restrict__ qkv, int heads, int kvh, const flo
 }  // namespace
 
 static int g_num_sms = 0;
-static int g_ctas_per_sm = 1;
 static int gv_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
-    const char* e = getenv("TRACE_B200_GEMV_CTAS_PER_SM");
-    if (e != nullptr && atoi(e) >= 1 && atoi(e) <= 2) g_ctas_per_sm = atoi(e);
   }
   return g_num_sms;
 }
@@ -657,18 +708,17 @@ int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, in
              const __half* gamma, float eps, int epi, cudaStream_t stream) {
   TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
   TB_CHECK(N % 2 == 0 && N >= 2, "GEMV rows must be even");
-  const int KP = pick_kp(K, B);
-  TB_CHECK(KP > 0, "GEMV K must be a multiple of 256");
-  TB_CHECK(!(pro == 1 && KP != K), "fused RMSNorm needs the whole row staged (K <= 4096)");
-  TB_CHECK(ldx % 8 == 0, "activation pitch must be 16-byte aligned");
-  const int grid = gemv_grid(N, gv_sms(), g_ctas_per_sm);
-  const size_t smem = gemv_smem(KP, B, N, grid);
-  TB_CHECK(smem <= 220 * 1024, "GEMV shared memory budget exceeded");
+  TB_CHECK(ldx % 8 == 0 && K % 256 == 0, "GEMV K must be a multiple of 256 and the activation pitch 16-byte aligned");
+  TB_CHECK((reinterpret_cast<uintptr_t>(W) & 15) == 0, "weights must be 16-byte aligned");
+  GvPlan p;
+  if (gemv_plan(N, K, B, 0, gv_sms(), &p)) return 1;
+  TB_CHECK(!(pro == 1 && p.KP != K), "fused RMSNorm needs the whole row staged (K <= 4096)");
 #define TB_GV(P, E)                                                                                              \
   do {                                                                                                           \
     static size_t cached = 0;                                                                                    \
-    if (ensure_smem(gemv_kernel<P, E>, smem, &cached)) return 1;                                                 \
-    if (launch_pdl(gemv_kernel<P, E>, dim3(grid), dim3(GV_THREADS), smem, stream, W, x, ldx, out, ldo, B, N, K, KP, gamma, eps)) return 1; \
+    if (ensure_smem(gemv_kernel<P, E>, p.smem, &cached)) return 1;                                               \
+    if (launch_pdl(gemv_kernel<P, E>, dim3(p.grid), dim3(GV_THREADS), p.smem, stream, W, x, ldx, out, ldo, B, N, K, p.KP, p.KS, \
+                   p.max_tiles, p.stages, gamma, eps)) return 1;                                                 \
   } while (0)
   if (pro == 0 && epi == 0) TB_GV(0, 0);
   else if (pro == 0 && epi == 1) TB_GV(0, 1);
@@ -681,7 +731,7 @@ int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, in
   return 0;
 }
 
-int head_gemv_ncand() { return gemv_grid(1 << 30, gv_sms(), g_ctas_per_sm); }
+int head_gemv_ncand() { return gemv_grid(1 << 30, gv_sms()); }
 
 int attn_decode(const __half* qkv, int B, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
                 __half* k_pool, __half* v_pool, const int32_t* block_table, int max_pages, int page_size,
@@ -703,12 +753,13 @@ int head_gemv(const __half* Wh, const __half* x, int ldx, int B, int n_valid, in
               cudaStream_t stream) {
   TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
   TB_CHECK(Npad % 2 == 0 && K % 256 == 0 && K <= 4096, "head GEMV shape");
-  const int grid = head_gemv_ncand();
-  const size_t smem = gemv_smem(K, B, Npad, grid);
+  GvPlan p;
+  if (gemv_plan(Npad, K, B, K, gv_sms(), &p)) return 1;
+  TB_CHECK(p.grid == head_gemv_ncand(), "head GEMV grid mismatch");
   static size_t cached = 0;
-  if (ensure_smem(head_gemv_kernel, smem, &cached)) return 1;
-  return launch_pdl(head_gemv_kernel, dim3(grid), dim3(GV_THREADS), smem, stream, Wh, x, ldx, B, n_valid, Npad, K, gamma, eps, vocab,
-                    static_cast<const int32_t*>(st.heads), cand_val, cand_idx, logits_out);
+  if (ensure_smem(head_gemv_kernel, p.smem, &cached)) return 1;
+  return launch_pdl(head_gemv_kernel, dim3(p.grid), dim3(GV_THREADS), p.smem, stream, Wh, x, ldx, B, n_valid, Npad, K, p.KS,
+                    p.max_tiles, p.stages, gamma, eps, vocab, static_cast<const int32_t*>(st.heads), cand_val, cand_idx, logits_out);
 }
 
 int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, int B, int vocab, int eos, int pad,
