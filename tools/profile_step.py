@@ -36,4 +36,6 @@ for i in range(a.warm + 1):
     out = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=clips, modal_list=["video"] * a.batch,
                          video_timestamps=stamps, heads=[1] * a.batch, do_sample=False, max_new_tokens=a.max_new, pad_token_id=2)
 torch.cuda.synchronize()
-print("ids", out.tolist(), "decode timing", model.engine.last_decode_timing())
+ms, st = model.engine.last_decode_timing()
+print("ids", out.tolist()[0][:16])
+print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f}")

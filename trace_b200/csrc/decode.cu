@@ -283,7 +283,11 @@ int gemv_plan(int N, int K, int B, int kp_force, int num_sms, GvPlan* p) {
   const size_t fixed = static_cast<size_t>(B) * (p->KP + XS_PAD) * 2 + static_cast<size_t>(p->max_tiles) * GV_WARPS * GV_TILE * 8 * 4 +
                        (GV_WARPS * GV_MAXB + GV_MAXB) * 4 + 2 * GV_MAXSTAGES * 8 + 128;
   const size_t stage = static_cast<size_t>(GV_TILE) * (p->KS + WS_PAD) * 2;
-  const size_t budget = 200 * 1024;
+  static size_t budget = 0;
+  if (budget == 0) {
+    const char* e = getenv("TRACE_B200_GEMV_SMEM_KB");
+    budget = static_cast<size_t>((e != nullptr && atoi(e) >= 48 && atoi(e) <= 220) ? atoi(e) : 200) * 1024;
+  }
   TB_CHECK(fixed + 2 * stage <= budget, "GEMV shared memory budget exceeded");
   int st = static_cast<int>((budget - fixed) / stage);
   if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;

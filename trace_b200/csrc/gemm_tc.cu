@@ -24,7 +24,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 halves = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / UMMA / TMEM alloc / spare ; warps 4-11: epilogue (2 per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -48,6 +49,19 @@ struct EpiParams {
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
+// Grouped rasterisation: consecutive tile ids walk all N-tiles of a band of `gm` M-tiles before moving to the next
+// band, so one wave of CTAs re-uses each A tile tiles_n times and each W tile gm times out of L2 (a plain m-fastest
+// order re-streams the whole A matrix from HBM once per N-tile when A > L2, e.g. the 151 MB fc2 input).
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int gm, int& m, int& n) {
+  const int per_band = gm * tiles_n;
+  const int band = tile / per_band;
+  const int in_band = tile - band * per_band;
+  const int m0 = band * gm;
+  const int rows = min(gm, tiles_m - m0);
+  m = m0 + in_band % rows;
+  n = in_band / rows;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -67,6 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  int gm = static_cast<int>(gridDim.x) / tiles_n;
+  gm = gm < 1 ? 1 : gm;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -79,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -95,8 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM;
-        const int n0 = (tile / tiles_m) * BN;
+        int tm, tn;
+        tile_coords(tile, tiles_m, tiles_n, gm, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -142,23 +159,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;                       // TMEM lane quarter == warp_id % 4
+    const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
+    const int half = (warp - 4) >> 2;             // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * BN;
+      int tm, tn;
+      tile_coords(tile, tiles_m, tiles_n, gm, tm, tn);
+      const int m0 = tm * BM, n0 = tn * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {                   // all TMEM reads of this stage are done -> release it
+        if (c == (half + 1) * (BN / 64) - 1) {    // this warp's TMEM reads of the stage are done -> release its share
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
