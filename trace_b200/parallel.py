@@ -32,7 +32,8 @@ def encode_frames_sharded(engine, frames: torch.Tensor, B: int, T: int, group) -
     fr = frames.view(B, T, *frames.shape[1:])[:, lo:hi].reshape(B * (hi - lo), *frames.shape[1:]).contiguous()
     local = engine.encode_frames(fr)                                   # [B*(T/G), 8, H]
     local = local.view(B, hi - lo, local.shape[1], local.shape[2])
-    gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    gathered = torch.empty((world * B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)   # concatenation along dim 0, rank-major
+    gathered = gathered.view(world, B, *local.shape[1:])
     # [G, B, T/G, 8, H] -> [B, G, T/G, 8, H] -> [B*T, 8, H]
     return gathered.permute(1, 0, 2, 3, 4).reshape(B * T, local.shape[2], local.shape[3]).contiguous()
