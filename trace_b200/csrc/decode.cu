@@ -17,204 +17,10 @@
 // once per CTA in shared memory.  Algorithmic bytes per launch = N*K*2 (+ B*(K+N)*2).
 #include "common.cuh"
 #include "kernels.h"
+#include "decode_dev.cuh"
 
 namespace tb {
 namespace {
-
-constexpr int GV_CONS = 256;            // 8 consumer warps (MMA + epilogue)
-constexpr int GV_THREADS = GV_CONS + 32; // + 1 producer warp (TMA bulk copies)
-constexpr int GV_WARPS = 8;
-constexpr int GV_TILE = 16;              // rows per MMA tile
-constexpr int GV_MAXB = 8;
-constexpr int GV_MAXSTAGES = 8;
-constexpr int XS_PAD = 32;               // halves; row pitch = KP*2 + 64 bytes -> conflict-free 16-byte fragment reads
-constexpr int WS_PAD = 32;               // same trick for the weight stages
-
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // consumer warps only
-
-// Balanced static partition: rows are dealt to the CTAs in units of 2 (SwiGLU pairs stay together), so every
-// CTA streams the same number of weight bytes (+-2 rows) whatever N is -- no wave quantisation.
-__device__ __forceinline__ void cta_rows(int N, int& r0, int& r1) {
-  const long long U = N / 2;
-  r0 = static_cast<int>(U * blockIdx.x / gridDim.x) * 2;
-  r1 = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * 2;
-}
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// ---- activation staging (+ optional RMSNorm) into shared memory: xs[b][k], b < B, k in [k0, k0+KP) ----
-// executed by the 256 consumer threads only
-template <int PRO>
-__device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, int B, int k0, int KP, int K,
-                                        const __half* gamma, float eps, float* s_red) {
-  const int tid = threadIdx.x;
-  const int pitch = KP + XS_PAD;
-  if (PRO == 1) {
-    // HF MistralRMSNorm: fp32 mean of squares over the full row (KP == K)
-    float ss[GV_MAXB];
-#pragma unroll
-    for (int b = 0; b < GV_MAXB; ++b) {
-      ss[b] = 0.f;
-      if (b < B) {
-        for (int i = tid; i < K / 8; i += GV_CONS) {
-          uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + i * 8);
-          float2 a = unpack_half2(u.x), c = unpack_half2(u.y), d = unpack_half2(u.z), e = unpack_half2(u.w);
-          ss[b] += a.x * a.x + a.y * a.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y + e.x * e.x + e.y * e.y;
-        }
-        ss[b] = warp_sum(ss[b]);
-      }
-    }
-    const int w = tid >> 5, l = tid & 31;
-    if (l == 0)
-#pragma unroll
-      for (int b = 0; b < GV_MAXB; ++b) s_red[w * GV_MAXB + b] = ss[b];
-    cons_sync();
-    if (tid < GV_MAXB) {
-      float t = 0.f;
-      for (int i = 0; i < GV_WARPS; ++i) t += s_red[i * GV_MAXB + tid];
-      s_red[GV_WARPS * GV_MAXB + tid] = rsqrtf(t / K + eps);
-    }
-    cons_sync();
-  }
-  for (int b = 0; b < B; ++b) {
-    const float rstd = (PRO == 1) ? s_red[GV_WARPS * GV_MAXB + b] : 1.f;
-    for (int i = tid; i < KP / 8; i += GV_CONS) {
-      uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8);
-      if (PRO == 1) {
-        uint4 gm = *reinterpret_cast<const uint4*>(gamma + k0 + i * 8);
-        uint32_t* up = &u.x;
-        const uint32_t* gp = &gm.x;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 v = unpack_half2(up[j]);
-          float2 gg = unpack_half2(gp[j]);
-          // weight * (x*rstd).to(fp16) : two roundings as in the reference
-          up[j] = pack_half2(gg.x * __half2float(__float2half_rn(v.x * rstd)), gg.y * __half2float(__float2half_rn(v.y * rstd)));
-        }
-      }
-      *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = u;
-    }
-  }
-}
-
-// Shared-memory carve-up of a GEMV CTA.
-struct GvSmem {
-  __half* xs;          // [B][KP + XS_PAD]
-  float* s_red;        // rmsnorm scratch
-  float* s_part;       // [tiles][8 warps][16 rows][8 batch]
-  uint64_t* full;      // [stages]
-  uint64_t* empty;     // [stages]
-  __half* ws;          // [stages][16][KS + WS_PAD]
-};
-__device__ __forceinline__ GvSmem gv_carve(uint8_t* smem, int B, int KP, int KS, int max_tiles, int stages) {
-  GvSmem m;
-  size_t off = 0;
-  m.ws = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(stages) * GV_TILE * (KS + WS_PAD) * 2;
-  m.xs = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(B) * (KP + XS_PAD) * 2;
-  m.s_part = reinterpret_cast<float*>(smem + off); off += static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
-  m.s_red = reinterpret_cast<float*>(smem + off); off += (GV_WARPS * GV_MAXB + GV_MAXB) * 4;
-  m.full = reinterpret_cast<uint64_t*>(smem + off); off += GV_MAXSTAGES * 8;
-  m.empty = reinterpret_cast<uint64_t*>(smem + off);
-  return m;
-}
-
-// ---- producer warp: streams rows [vlo,vhi) of the tiles of [r0,r1) in (phase, tile, k-stage) order ----------
-// One bulk copy per valid row per stage (lanes 0..15 issue them in one instruction); the copies do not depend on
-// the previous kernel, so this warp never executes griddepcontrol.wait and runs up to `stages` stages ahead.
-__device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
-                                              int vhi, const GvSmem& m, int stages) {
-  const int lane = threadIdx.x & 31;
-  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
-  const int pitch = KS + WS_PAD;
-  int s = 0;
-  uint32_t ph = 0;
-  for (int k0 = 0; k0 < K; k0 += KP) {
-    for (int tile = 0; tile < ntile; ++tile) {
-      const int tr0 = r0 + tile * GV_TILE;
-      const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
-      if (lo >= hi) continue;                      // no row of this tile is needed (head GEMV on a narrow head)
-      for (int ks = 0; ks < KP; ks += KS) {
-        mbar_wait(&m.empty[s], ph ^ 1);
-        if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
-        __syncwarp();
-        const int row = tr0 + lane;
-        if (lane < GV_TILE && row >= lo && row < hi)
-          bulk_g2s(m.ws + (static_cast<size_t>(s) * GV_TILE + lane) * pitch, W + static_cast<size_t>(row) * K + k0 + ks, KS * 2, &m.full[s]);
-        if (++s == stages) { s = 0; ph ^= 1; }
-      }
-    }
-  }
-}
-
-// ---- consumer warps: MMA over the staged tiles; partial sums per (tile, warp) in shared memory ---------------
-__device__ __forceinline__ void gemv_consume_phase(int k0, int KP, int KS, int r0, int r1, int vlo, int vhi, const GvSmem& m,
-                                                   int B, int stages, int& s, uint32_t& ph) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
-  const int ksw = KS / GV_WARPS;                  // columns of a stage owned by this warp (multiple of 32)
-  const int nch = ksw / 32;
-  const int wpitch = KS + WS_PAD;
-  const bool xok = g < B;
-  for (int tile = 0; tile < ntile; ++tile) {
-    const int tr0 = r0 + tile * GV_TILE;
-    float* p = m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * 8);
-    if (max(tr0, vlo) >= min(tr0 + GV_TILE, vhi)) {
-      if (k0 == 0) { p[g * 8 + 2 * t] = 0.f; p[g * 8 + 2 * t + 1] = 0.f; p[(g + 8) * 8 + 2 * t] = 0.f; p[(g + 8) * 8 + 2 * t + 1] = 0.f; }
-      continue;
-    }
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ks = 0; ks < KP; ks += KS) {
-      mbar_wait(&m.full[s], ph);
-      const __half* wa = m.ws + (static_cast<size_t>(s) * GV_TILE + g) * wpitch + warp * ksw + t * 8;
-      const __half* wb = wa + 8 * wpitch;
-      const __half* xp = m.xs + g * (KP + XS_PAD) + ks + warp * ksw + t * 8;
-#pragma unroll 4
-      for (int ch = 0; ch < nch; ++ch) {
-        const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
-        const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
-        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
-        mma_16816(c, a.x, b.x, a.y, b.y, xv.x, xv.y);
-        mma_16816(c, a.z, b.z, a.w, b.w, xv.z, xv.w);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&m.empty[s]);
-      if (++s == stages) { s = 0; ph ^= 1; }
-    }
-    if (k0 > 0) {
-      p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
-      p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
-    } else {
-      p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
-      p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
-    }
-  }
-}
-
-// sum of the 8 warps' partials for output `idx` = tile*128 + row*8 + n
-__device__ __forceinline__ float gemv_out(const float* s_part, int idx) {
-  const int tile = idx >> 7, rn = idx & 127;
-  const float* p = s_part + tile * (GV_WARPS * GV_TILE * 8) + rn;
-  float v = 0.f;
-#pragma unroll
-  for (int w = 0; w < GV_WARPS; ++w) v += p[w * (GV_TILE * 8)];
-  return v;
-}
-
-__device__ __forceinline__ void gv_init_barriers(const GvSmem& m, int stages) {
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < stages; ++i) {
-      mbar_init(&m.full[i], 1);
-      mbar_init(&m.empty[i], GV_WARPS);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-}
 
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(GV_THREADS, 1)
@@ -227,7 +33,9 @@ gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx,
   gv_init_barriers(m, stages);
   pdl_launch_dependents();
   if (threadIdx.x >= GV_CONS) {
-    gemv_producer(W, K, KP, KS, r0, r1, r0, r1, m, stages);    // weights never depend on the previous kernel
+    int ps = 0;
+    uint32_t pph = 0;
+    gemv_producer(W, K, KP, KS, r0, r1, r0, r1, m, stages, ps, pph);    // weights never depend on the previous kernel
     return;
   }
   pdl_wait();                                                  // activations do
@@ -326,12 +134,6 @@ int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaS
 // ------------------------------------------------------------------------------------------------
 // head GEMV: logits + mask + argmax candidates
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void head_range(int h, int vocab, int& lo, int& hi) {
-  if (h <= 0) { lo = 0; hi = vocab + 1; }                 // text head (0) or text-only mode (-1)
-  else if (h == 1) { lo = vocab + 1; hi = vocab + 14; }   // time head
-  else { lo = vocab + 14; hi = vocab + 27; }              // score head
-}
-
 __global__ void __launch_bounds__(GV_THREADS, 1)
 head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx, int B, int n_valid, int Npad, int K,
                  int KS, int max_tiles, int stages, const __half* __restrict__ gamma, float eps, int vocab,
@@ -360,7 +162,9 @@ head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int
   }
   const int vlo = max(ulo, r0), vhi = min(uhi, r1);   // only rows some batch row decodes from are read at all
   if (threadIdx.x >= GV_CONS) {
-    if (vlo < vhi) gemv_producer(W, K, K, KS, r0, r1, vlo, vhi, m, stages);
+    int ps = 0;
+    uint32_t pph = 0;
+    if (vlo < vhi) gemv_producer(W, K, K, KS, r0, r1, vlo, vhi, m, stages, ps, pph);
     return;
   }
   const int n = threadIdx.x & 7;

@@ -1,0 +1,603 @@
+// The whole decode step as ONE persistent kernel (one CTA per SM, 8 consumer warps + 1 producer warp):
+//
+//   for each of the 32 layers: RMSNorm+QKV -> RoPE/KV-append/attention -> O(+residual) -> RMSNorm+gate/up(SwiGLU) -> down(+residual)
+//   then final RMSNorm + active-head logits + masked argmax, and (CTA 0) the token bookkeeping / head switch / next embedding.
+//
+// Why: per-op kernels leave the HBM pipe idle at every kernel boundary (launch ramp, activation staging, epilogue:
+// 5-7 us per boundary x 162 boundaries per token against a 2.2 ms HBM floor).  Here the producer warp of every CTA
+// streams that CTA's weight rows with cp.async.bulk into an mbarrier ring and NEVER waits for activations: while the
+// consumer warps sit in a grid barrier or stage the next activation vector, the ring keeps filling with the next
+// phase's weights, so the weight stream is continuous across phase and layer boundaries.  Phases are separated by a
+// grid-wide barrier (atomic counter, consumers only); activations written by other CTAs are re-read with ld.global.cg.
+//
+// Replaces: trace_mistral.py:114-264 forward (decoder layers via HF MistralModel, heads :190-200, mask :244-252),
+// :336-344 head switch, trace_arch.py:345-375 embedding dispatch, HF greedy argmax -- for one generated token.
+#include "common.cuh"
+#include "decode_dev.cuh"
+#include "kernels.h"
+
+namespace tb {
+namespace {
+
+constexpr int MG_G = 4;       // query heads per kv head
+constexpr int MG_HD = 128;
+
+// ---- grid barrier (consumer warps only; the producer warp never synchronises with anything but its ring) ----
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
+  cons_sync();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_u32(bar) < target) { }
+    __threadfence();
+  }
+  cons_sync();
+}
+
+// epilogues of the GEMV phases (256 consumer threads, after the partials are complete)
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo) {
+  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+  for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+    const float v = gemv_out(m.s_part, idx);
+    const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
+    if (EPI == 2) {
+      const float partner = __shfl_xor_sync(0xffffffffu, v, 8);
+      if ((row & 1) == 0 && n < B && row < r1) __stcg(out + static_cast<size_t>(n) * ldo + (row >> 1), __float2half_rn(silu_f(v) * partner));
+    } else if (n < B && row < r1) {
+      __half* o = out + static_cast<size_t>(n) * ldo + row;
+      if (EPI == 1) __stcg(o, __float2half_rn(v + __half2float(__ldcg(o))));
+      else __stcg(o, __float2half_rn(v));
+    }
+  }
+}
+
+struct MegaLayer {
+  const __half *ln1, *qkv_w, *o_w, *ln2, *gateup_w, *down_w;
+  __half *k_pool, *v_pool;
+};
+
+struct MegaParams {
+  int B, H, qkvw, qd, ffn, layers, heads, kvh, vocab, head_rows, n_valid;
+  float eps;
+  const MegaLayer* L;                 // device array [layers]
+  const __half *final_norm, *head_w;
+  __half *x, *qkv, *attn, *act;       // decode activations [B, .]
+  const float *cos_tab, *sin_tab;
+  const int32_t* block_table;
+  int max_pages, page_size;
+  float *part_o, *part_ml;
+  int32_t* counters;
+  int nsplit, chunk_max;
+  float* cand_val;
+  int32_t* cand_idx;
+  float* logits_out;
+  const __half *embed, *time_tab, *score_tab, *sync_tab;
+  int eos, pad;
+  DecodeState st;
+  unsigned *gbar, *gexit;
+  int kp_qkv, ks_qkv, kp_o, ks_o, kp_gu, ks_gu, kp_dn, ks_dn, kp_hd, ks_hd;
+  int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+};
+
+// ------------------------------------------------------------------------------------------------
+// attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, int b, int kv, int split, float* scratch) {
+  float* qs = scratch;                           // [4][128]
+  float* knew = qs + MG_G * MG_HD;               // [128]
+  float* vnew = knew + MG_HD;                    // [128]
+  float* red = vnew + MG_HD;                     // [8 warps][4][128]
+  float* sc = red + GV_WARPS * MG_G * MG_HD;     // [4][chunk_max + 1]
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int heads = p.heads, kvh = p.kvh, nsplit = p.nsplit, page_size = p.page_size;
+  const int t = p.st.pos[b];
+  const int slot = p.st.slot_ids[b];
+  const int32_t* table = p.block_table + static_cast<size_t>(slot) * p.max_pages;
+  const __half* row = p.qkv + static_cast<size_t>(b) * p.qkvw;
+  const float scale = rsqrtf(static_cast<float>(MG_HD));
+  const int cpitch = p.chunk_max + 1;
+  const float* cs = p.cos_tab + static_cast<size_t>(t) * (MG_HD / 2);
+  const float* sn = p.sin_tab + static_cast<size_t>(t) * (MG_HD / 2);
+  for (int i = tid; i < MG_G * (MG_HD / 2); i += GV_CONS) {
+    const int h = i / (MG_HD / 2), d = i % (MG_HD / 2);
+    const __half* qp = row + (kv * MG_G + h) * MG_HD;
+    const float a = __half2float(__ldcg(qp + d)), c2 = __half2float(__ldcg(qp + d + MG_HD / 2));
+    qs[h * MG_HD + d] = __half2float(__float2half_rn(a * cs[d] - c2 * sn[d])) * scale;
+    qs[h * MG_HD + d + MG_HD / 2] = __half2float(__float2half_rn(c2 * cs[d] + a * sn[d])) * scale;
+  }
+  if (split == 0) {
+    const int page = table[t / page_size], poff = t % page_size;
+    const size_t dst = ((static_cast<size_t>(page) * kvh + kv) * page_size + poff) * MG_HD;
+    if (tid < MG_HD / 2) {
+      const __half* kp = row + (heads + kv) * MG_HD;
+      const float a = __half2float(__ldcg(kp + tid)), c2 = __half2float(__ldcg(kp + tid + MG_HD / 2));
+      const __half ra = __float2half_rn(a * cs[tid] - c2 * sn[tid]);
+      const __half rb = __float2half_rn(c2 * cs[tid] + a * sn[tid]);
+      L.k_pool[dst + tid] = ra;
+      L.k_pool[dst + tid + MG_HD / 2] = rb;
+      knew[tid] = __half2float(ra);
+      knew[tid + MG_HD / 2] = __half2float(rb);
+    } else if (tid < MG_HD) {
+      const int d = (tid - MG_HD / 2) * 2;
+      const __half* vp = row + (heads + kvh + kv) * MG_HD;
+      const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(vp + d));
+      *reinterpret_cast<unsigned*>(L.v_pool + dst + d) = u;
+      const float2 f = unpack_half2(u);
+      vnew[d] = f.x;
+      vnew[d + 1] = f.y;
+    }
+  }
+  cons_sync();
+  int chunk = (t + nsplit - 1) / nsplit;
+  chunk = (chunk + 31) & ~31;
+  const int start = split * chunk;
+  const int end = min(start + chunk, t);
+  const int nloc = max(end - start, 0);
+  // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
+  for (int base = warp * 16; base < nloc; base += GV_WARPS * 16) {
+    const int j = base + (lane >> 1);
+    const int hf = lane & 1;
+    const bool valid = j < nloc;
+    const int key = start + (valid ? j : 0);
+    const int page = table[key / page_size];
+    const __half* kr = L.k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
+    uint4 kreg[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+    float acc[MG_G] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float kf[8];
+      float2 p0 = unpack_half2(kreg[c].x), p1 = unpack_half2(kreg[c].y), p2 = unpack_half2(kreg[c].z), p3 = unpack_half2(kreg[c].w);
+      kf[0] = p0.x; kf[1] = p0.y; kf[2] = p1.x; kf[3] = p1.y; kf[4] = p2.x; kf[5] = p2.y; kf[6] = p3.x; kf[7] = p3.y;
+#pragma unroll
+      for (int h = 0; h < MG_G; ++h) {
+        const float4 q0 = *reinterpret_cast<const float4*>(qs + h * MG_HD + hf * 64 + c * 8);
+        const float4 q1 = *reinterpret_cast<const float4*>(qs + h * MG_HD + hf * 64 + c * 8 + 4);
+        acc[h] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < MG_G; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+    if (valid && hf == 0) {
+#pragma unroll
+      for (int h = 0; h < MG_G; ++h) sc[h * cpitch + j] = acc[h];
+    }
+  }
+  int ntot = nloc;
+  if (split == 0) {
+    if (warp < MG_G) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d += qs[warp * MG_HD + lane * 4 + i] * knew[lane * 4 + i];
+      d = warp_sum(d);
+      if (lane == 0) sc[warp * cpitch + nloc] = d;
+    }
+    ntot = nloc + 1;
+  }
+  cons_sync();
+  float mx = -INFINITY, l = 0.f;
+  if (warp < MG_G) {
+    float* s = sc + warp * cpitch;
+    for (int j = lane; j < ntot; j += 32) mx = fmaxf(mx, s[j]);
+    mx = warp_max(mx);
+    for (int j = lane; j < ntot; j += 32) {
+      const float pr = __expf(s[j] - mx);
+      s[j] = pr;
+      l += pr;
+    }
+    l = warp_sum(l);
+  }
+  cons_sync();
+  // phase B: lane <-> 4 dims, warps stride over keys, 8 keys per pass with the loads up front
+  float o[MG_G][4];
+#pragma unroll
+  for (int h = 0; h < MG_G; ++h) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
+  for (int j0 = warp; j0 < nloc; j0 += GV_WARPS * 8) {
+    uint2 vreg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * GV_WARPS;
+      const int key = start + (j < nloc ? j : 0);
+      const int page = table[key / page_size];
+      vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * GV_WARPS;
+      if (j < nloc) {
+        const float2 v0 = unpack_half2(vreg[u].x), v1 = unpack_half2(vreg[u].y);
+#pragma unroll
+        for (int h = 0; h < MG_G; ++h) {
+          const float pr = sc[h * cpitch + j];
+          o[h][0] += pr * v0.x; o[h][1] += pr * v0.y; o[h][2] += pr * v1.x; o[h][3] += pr * v1.y;
+        }
+      }
+    }
+  }
+  if (split == 0 && warp == 0) {
+#pragma unroll
+    for (int h = 0; h < MG_G; ++h) {
+      const float pr = sc[h * cpitch + nloc];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[h][i] += pr * vnew[lane * 4 + i];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < MG_G; ++h)
+    *reinterpret_cast<float4*>(red + (warp * MG_G + h) * MG_HD + lane * 4) = make_float4(o[h][0], o[h][1], o[h][2], o[h][3]);
+  cons_sync();
+  const size_t pbase = (static_cast<size_t>(b) * kvh + kv) * nsplit + split;
+  if (tid < 128) {
+    float4 a = *reinterpret_cast<const float4*>(red + tid * 4);
+#pragma unroll
+    for (int w = 1; w < GV_WARPS; ++w) {
+      const float4 x4 = *reinterpret_cast<const float4*>(red + w * MG_G * MG_HD + tid * 4);
+      a.x += x4.x; a.y += x4.y; a.z += x4.z; a.w += x4.w;
+    }
+    __stcg(reinterpret_cast<float4*>(p.part_o + pbase * (MG_G * MG_HD) + tid * 4), a);
+  }
+  if (warp < MG_G && lane == 0) {
+    __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2, mx);
+    __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2 + 1, l);
+  }
+  __threadfence();
+  cons_sync();
+  if (tid == 0) s_last = (atomicAdd(&p.counters[b * kvh + kv], 1) == nsplit - 1);
+  cons_sync();
+  if (s_last) {     // the last split of this (row, kv head) combines the partials -> attn [B, heads*128] fp16
+    __threadfence();
+    if (tid < 128) {
+      const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
+      const int h = tid >> 5;
+      float M = -INFINITY;
+      for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2));
+      float Lsum = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < nsplit; ++s) {
+        const float ms = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2);
+        const float ls = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2 + 1);
+        if (ls == 0.f) continue;
+        const float w = __expf(ms - M);
+        Lsum += w * ls;
+        const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + s) * (MG_G * MG_HD) + tid * 4));
+        acc.x += w * po.x; acc.y += w * po.y; acc.z += w * po.z; acc.w += w * po.w;
+      }
+      const float inv = 1.f / Lsum;
+      uint2 pk;
+      pk.x = pack_half2(acc.x * inv, acc.y * inv);
+      pk.y = pack_half2(acc.z * inv, acc.w * inv);
+      __stcg(reinterpret_cast<uint2*>(p.attn + static_cast<size_t>(b) * heads * MG_HD + (kv * MG_G) * MG_HD + tid * 4), pk);
+    }
+    if (tid == 0) p.counters[b * kvh + kv] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize (CTA 0, 256 consumer threads)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finalize_step(const MegaParams& p, int ncand) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  __shared__ int s_tok[GV_MAXB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const DecodeState& st = p.st;
+  const int step = *st.step;
+  for (int b = 0; b < p.B; ++b) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < ncand; i += GV_CONS) {
+      const float v = __ldcg(p.cand_val + b * ncand + i);
+      const int ix = __ldcg(p.cand_idx + b * ncand + i);
+      if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+    cons_sync();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi)) { bv = s_v[w]; bi = s_i[w]; }
+      const int tok = st.finished[b] ? p.pad : bi;
+      if (step < st.max_new) st.out_ids[static_cast<int64_t>(b) * st.max_new + step] = tok;
+      if (!st.finished[b] && tok == p.eos) st.finished[b] = 1;
+      if (st.heads[b] >= 0) {
+        if (tok == p.vocab) st.heads[b] = 1;
+        else if (tok == p.vocab + 1) st.heads[b] = 2;
+        else if (tok == p.vocab + 14) st.heads[b] = 0;
+      }
+      st.pos[b] += 1;
+      s_tok[b] = tok;
+    }
+    cons_sync();
+  }
+  if (tid == 0) {
+    int all = 1;
+    for (int b = 0; b < p.B; ++b) all &= st.finished[b];
+    *st.step = step + 1;
+    if (all && *st.done_step == 0) *st.done_step = step + 1;
+  }
+  for (int b = 0; b < p.B; ++b) {
+    const int tok = s_tok[b];
+    const __half* src;
+    if (tok == p.vocab) src = p.sync_tab;
+    else if (tok > p.vocab && tok < p.vocab + 14) src = p.time_tab + static_cast<size_t>(tok - p.vocab - 1) * p.H;
+    else if (tok >= p.vocab + 14) src = p.score_tab + static_cast<size_t>(tok - p.vocab - 14) * p.H;
+    else src = p.embed + static_cast<size_t>(tok % p.vocab) * p.H;
+    for (int i = tid; i < p.H / 8; i += GV_CONS)
+      reinterpret_cast<uint4*>(p.x + static_cast<size_t>(b) * p.H)[i] = reinterpret_cast<const uint4*>(src)[i];
+  }
+}
+
+// one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
+template <int PRO, int EPI>
+__device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
+                                                int N, int K, int KP, int KS, const __half* gamma, int& s, uint32_t& ph) {
+  int r0, r1;
+  cta_rows(N, r0, r1);
+  for (int k0 = 0; k0 < K; k0 += KP) {
+    if (k0 > 0) cons_sync();
+    stage_x<PRO>(m.xs, xin, ldx, p.B, k0, KP, K, gamma, p.eps, m.s_red);
+    cons_sync();
+    // the staged row pitch is KP + XS_PAD: gemv_consume_phase derives it from KP
+    gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages, s, ph);
+  }
+  cons_sync();
+  gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
+}
+
+__global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve with the largest stage (KS = 1024) and the reserved activation capacity
+  GvSmem m;
+  {
+    size_t off = 0;
+    m.ws = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(p.stages) * GV_TILE * (1024 + WS_PAD) * 2;
+    m.xs = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(p.B) * p.xs_cap * 2;
+    m.s_part = reinterpret_cast<float*>(smem + off); off += static_cast<size_t>(p.max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
+    m.s_red = reinterpret_cast<float*>(smem + off); off += (GV_WARPS * GV_MAXB + GV_MAXB) * 4;
+    m.full = reinterpret_cast<uint64_t*>(smem + off); off += GV_MAXSTAGES * 8;
+    m.empty = reinterpret_cast<uint64_t*>(smem + off);
+    m.ws_stride = GV_TILE * (1024 + WS_PAD);   // fixed stage stride: phases with a smaller KS must not alias other stages
+  }
+  gv_init_barriers(m, p.stages);
+  const int ncta = gridDim.x;
+  // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
+  // late producer warp must not see the new values or it would stream rows that nobody consumes)
+  int hlo[GV_MAXB], hhi[GV_MAXB];
+  int ulo = 0x7fffffff, uhi = 0;
+#pragma unroll
+  for (int b = 0; b < GV_MAXB; ++b) {
+    hlo[b] = hhi[b] = 0;
+    if (b < p.B) {
+      head_range(p.st.heads[b], p.vocab, hlo[b], hhi[b]);
+      ulo = min(ulo, hlo[b]);
+      uhi = max(uhi, hhi[b]);
+    }
+  }
+
+  if (threadIdx.x >= GV_CONS) {
+    // ===================== producer warp: the whole step's weight stream =====================
+    int s = 0;
+    uint32_t ph = 0;
+    int r0, r1;
+    for (int l = 0; l < p.layers; ++l) {
+      const MegaLayer L = p.L[l];
+      cta_rows(p.qkvw, r0, r1);
+      gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph);
+      cta_rows(p.H, r0, r1);
+      gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph);
+      cta_rows(2 * p.ffn, r0, r1);
+      gemv_producer(L.gateup_w, p.H, p.kp_gu, p.ks_gu, r0, r1, r0, r1, m, p.stages, s, ph);
+      cta_rows(p.H, r0, r1);
+      gemv_producer(L.down_w, p.ffn, p.kp_dn, p.ks_dn, r0, r1, r0, r1, m, p.stages, s, ph);
+    }
+    // head: only the rows some batch row decodes from (heads[] was written by the previous step)
+    cta_rows(p.head_rows, r0, r1);
+    const int vlo = max(ulo, r0), vhi = min(uhi, r1);
+    if (vlo < vhi) gemv_producer(p.head_w, p.H, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.stages, s, ph);
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  unsigned target = 0;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int l = 0; l < p.layers; ++l) {
+    const MegaLayer L = p.L[l];
+    if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
+    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, L.ln1, s, ph);
+    grid_sync(p.gbar, target);                                                // q, k, v complete
+    {
+      const int items = p.B * p.kvh * p.nsplit;
+      for (int it = blockIdx.x; it < items; it += ncta) {
+        const int split = it % p.nsplit, kv = (it / p.nsplit) % p.kvh, b = it / (p.nsplit * p.kvh);
+        attn_item(p, L, b, kv, split, m.s_part);
+        cons_sync();
+      }
+    }
+    grid_sync(p.gbar, target);                                                // attention output complete
+    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, nullptr, s, ph);
+    grid_sync(p.gbar, target);
+    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, L.ln2, s, ph);
+    grid_sync(p.gbar, target);
+    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, nullptr, s, ph);
+  }
+  grid_sync(p.gbar, target);
+  // ---- heads: final RMSNorm + logits of the active ranges + argmax candidates ----
+  {
+    int r0, r1;
+    cta_rows(p.head_rows, r0, r1);
+    const int vlo = max(ulo, r0), vhi = min(uhi, r1);
+    const int n = threadIdx.x & 7;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+    __shared__ float s_cv[GV_WARPS][8];
+    __shared__ int s_ci[GV_WARPS][8];
+    if (vlo < vhi) {
+      stage_x<1>(m.xs, p.x, p.H, p.B, 0, p.kp_hd, p.H, p.final_norm, p.eps, m.s_red);
+      cons_sync();
+      gemv_consume_phase(0, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.B, p.stages, s, ph);
+      cons_sync();
+      int lo = 0, hi = 0;
+#pragma unroll
+      for (int b = 0; b < GV_MAXB; ++b) if (b == n) { lo = hlo[b]; hi = hhi[b]; }
+      for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+        const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+        float v = __half2float(__float2half_rn(gemv_out(m.s_part, idx)));
+        const bool act = (n < p.B) && r < r1 && r >= lo && r < hi;
+        if (!act) v = -INFINITY;
+        if (p.logits_out != nullptr && n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = v;
+        if (act && (v > bv || (v == bv && r < bi))) { bv = v; bi = r; }
+      }
+    } else if (p.logits_out != nullptr) {
+      for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+        const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+        if (n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
+    cons_sync();
+    if (threadIdx.x < p.B) {
+      float v = s_cv[0][threadIdx.x];
+      int i = s_ci[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < GV_WARPS; ++w) {
+        const float ov = s_cv[w][threadIdx.x];
+        const int oi = s_ci[w][threadIdx.x];
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+      }
+      __stcg(p.cand_val + threadIdx.x * ncta + blockIdx.x, v);
+      __stcg(p.cand_idx + threadIdx.x * ncta + blockIdx.x, i);
+    }
+  }
+  grid_sync(p.gbar, target);
+  if (blockIdx.x == 0) finalize_step(p, ncta);
+  // exit protocol: the last CTA to leave resets the barrier counters for the next launch
+  cons_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.gexit, 1u) == static_cast<unsigned>(ncta) - 1) {
+      *p.gbar = 0;
+      *p.gexit = 0;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace
+
+// host side ---------------------------------------------------------------------------------------------------
+struct MegaPlan {
+  MegaParams p;
+  size_t smem;
+  int grid;
+};
+
+static int pick_kp_cap(int K, int B, size_t cap_bytes) {
+  for (int kp = 16384; kp >= 256; kp -= 256)
+    if (K % kp == 0 && kp <= K && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= cap_bytes) return kp;
+  return 0;
+}
+static int pick_ks2(int KP) {
+  for (int ks = 1024; ks >= 256; ks -= 256)
+    if (KP % ks == 0) return ks;
+  return 0;
+}
+
+int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int max_ctx, int kvh, int num_sms, int* nsplit_out,
+                     int* chunk_max_out, int* kp_ks /*[10]*/, int* max_tiles_out, int* stages_out, int* xs_cap_out, size_t* smem_out) {
+  TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
+  const size_t xcap = 64 * 1024;
+  const int Ks[5] = {H, qd, H, ffn, H};
+  int kpmax = 0;
+  for (int i = 0; i < 5; ++i) {
+    int kp = pick_kp_cap(Ks[i], B, xcap);
+    TB_CHECK(kp > 0, "decode GEMV K must be a multiple of 256");
+    if (i == 0 || i == 2 || i == 4) TB_CHECK(kp == Ks[i], "fused RMSNorm needs the whole hidden row staged");
+    kp_ks[2 * i] = kp;
+    kp_ks[2 * i + 1] = pick_ks2(kp);
+    if (kp > kpmax) kpmax = kp;
+  }
+  const int Ns[5] = {qkvw, H, 2 * ffn, H, head_rows};
+  int max_tiles = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int rows = ((Ns[i] / 2 + num_sms - 1) / num_sms) * 2 + 2;
+    const int t = (rows + GV_TILE - 1) / GV_TILE;
+    if (t > max_tiles) max_tiles = t;
+  }
+  int nsplit = num_sms / (B * kvh);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 32) nsplit = 32;
+  const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
+  // attention scratch lives in the s_part region: qs + knew + vnew + red + sc
+  const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + static_cast<size_t>(MG_G) * (chunk_max + 1)) * 4;
+  size_t part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
+  while (part_bytes < attn_scratch) { ++max_tiles; part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4; }
+  const int xs_cap = kpmax + XS_PAD;
+  const size_t fixed = static_cast<size_t>(B) * xs_cap * 2 + part_bytes + (GV_WARPS * GV_MAXB + GV_MAXB) * 4 + 2 * GV_MAXSTAGES * 8 + 256;
+  const size_t stage = static_cast<size_t>(GV_TILE) * (1024 + WS_PAD) * 2;
+  const size_t budget = 224 * 1024;
+  TB_CHECK(fixed + 2 * stage <= budget, "decode step shared memory budget exceeded");
+  int st = static_cast<int>((budget - fixed) / stage);
+  if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;
+  *nsplit_out = nsplit;
+  *chunk_max_out = chunk_max;
+  *max_tiles_out = max_tiles;
+  *stages_out = st;
+  *xs_cap_out = xs_cap;
+  *smem_out = fixed + st * stage;
+  return 0;
+}
+
+int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
+  MegaParams p{};
+  p.B = a.B; p.H = a.H; p.qkvw = a.qkvw; p.qd = a.qd; p.ffn = a.ffn; p.layers = a.layers; p.heads = a.heads; p.kvh = a.kvh;
+  p.vocab = a.vocab; p.head_rows = a.head_rows; p.n_valid = a.n_valid; p.eps = a.eps;
+  p.L = reinterpret_cast<const MegaLayer*>(a.layer_table_dev);
+  p.final_norm = a.final_norm; p.head_w = a.head_w; p.x = a.x; p.qkv = a.qkv; p.attn = a.attn; p.act = a.act;
+  p.cos_tab = a.cos_tab; p.sin_tab = a.sin_tab; p.block_table = a.block_table; p.max_pages = a.max_pages; p.page_size = a.page_size;
+  p.part_o = a.part_o; p.part_ml = a.part_ml; p.counters = a.counters; p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
+  p.logits_out = a.logits_out; p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
+  p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
+  int kpks[10];
+  size_t smem = 0;
+  if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.max_tiles,
+                       &p.stages, &p.xs_cap, &smem))
+    return 1;
+  p.kp_qkv = kpks[0]; p.ks_qkv = kpks[1]; p.kp_o = kpks[2]; p.ks_o = kpks[3]; p.kp_gu = kpks[4]; p.ks_gu = kpks[5];
+  p.kp_dn = kpks[6]; p.ks_dn = kpks[7]; p.kp_hd = kpks[8]; p.ks_hd = kpks[9];
+  TB_CHECK(a.heads == a.kvh * MG_G && a.qd == a.heads * MG_HD, "fused decode step is specialised for 128-dim heads, 4 q heads per kv head");
+  static size_t cached = 0;
+  if (smem > cached) {
+    TB_CUDA(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cached = smem;
+  }
+  // every CTA must be resident at once (grid barriers): one CTA per SM by shared-memory footprint, grid = #SMs
+  decode_step_kernel<<<a.num_sms, GV_THREADS, smem, stream>>>(p);
+  TB_LAUNCH_OK();
+  return 0;
+}
+
+int decode_mega_layer_table_bytes() { return static_cast<int>(sizeof(MegaLayer)); }
+
+}  // namespace tb

@@ -86,6 +86,10 @@ struct trace_b200_ctx {
   cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   float last_decode_ms = 0.f;
   int last_decode_steps = 0;
+  // fused decode step (decode_mega.cu)
+  void* d_layer_table = nullptr;
+  unsigned* d_gbar = nullptr;
+  bool fused_decode = true;
 };
 
 namespace {
@@ -219,6 +223,11 @@ int allocate_all(trace_b200_ctx* ctx) {
       dalloc(ctx, &ctx->st.done_step, 1, true) || dalloc(ctx, &ctx->st.out_ids, static_cast<size_t>(kMaxB) * c.max_ctx, true) ||
       dalloc(ctx, &ctx->st.slot_ids, kMaxB, true))
     return 1;
+  if (dalloc(ctx, &ctx->d_gbar, 4, true)) return 1;
+  {
+    const char* env = getenv("TRACE_B200_DECODE_PEROP");
+    ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
+  }
   // ---- KV pool ----
   const size_t page_elems = static_cast<size_t>(c.kv_heads) * kPage * c.head_dim;
   ctx->k_pool.resize(c.layers);
@@ -406,6 +415,19 @@ int decode_nsplit(const trace_b200_ctx* ctx, int B) {
 int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out, cudaStream_t s) {
   const trace_b200_config& c = ctx->c;
   const int H = c.hidden, qd = c.heads * c.head_dim;
+  if (ctx->fused_decode) {
+    DecodeMegaArgs a{};
+    a.B = B; a.H = H; a.qkvw = ctx->qkvw; a.qd = qd; a.ffn = c.ffn; a.layers = c.layers; a.heads = c.heads; a.kvh = c.kv_heads;
+    a.vocab = c.vocab; a.head_rows = ctx->head_rows; a.n_valid = ctx->total_vocab; a.max_ctx = c.max_ctx; a.num_sms = ctx->num_sms;
+    a.eps = c.rms_eps; a.layer_table_dev = ctx->d_layer_table; a.final_norm = ctx->final_norm; a.head_w = ctx->head_w;
+    a.x = ctx->d_x; a.qkv = ctx->d_qkv; a.attn = ctx->d_attn; a.act = ctx->d_act; a.cos_tab = ctx->rope_cos; a.sin_tab = ctx->rope_sin;
+    a.block_table = ctx->d_block_table; a.max_pages = ctx->max_pages_seq; a.page_size = kPage; a.part_o = ctx->d_part_o;
+    a.part_ml = ctx->d_part_ml; a.counters = ctx->d_counters; a.cand_val = ctx->d_cand_val; a.cand_idx = ctx->d_cand_idx;
+    a.logits_out = logits_out; a.embed = ctx->embed; a.time_tab = ctx->time_tab; a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab;
+    a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar;
+    RUN(decode_step_fused(a, s));
+    return 0;
+  }
   const int nsplit = decode_nsplit(ctx, B);
   for (int i = 0; i < c.layers; ++i) {
     const LlmLayer& l = ctx->llm[i];
@@ -488,6 +510,23 @@ int trace_b200_load_weight(trace_b200_ctx* ctx, const char* hf_name, const void*
 int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
   TB_CHECK(ctx != nullptr, "null context");
   for (const std::string& n : ctx->expected) TB_CHECK(ctx->loaded.count(n) == 1, "missing weight " + n);
+  {
+    TB_CHECK(decode_mega_layer_table_bytes() == 8 * static_cast<int>(sizeof(void*)), "layer table layout mismatch");
+    std::vector<const void*> tab;
+    for (int i = 0; i < ctx->c.layers; ++i) {
+      const LlmLayer& l = ctx->llm[i];
+      for (const void* q : {static_cast<const void*>(l.ln1), static_cast<const void*>(l.qkv_w), static_cast<const void*>(l.o_w),
+                            static_cast<const void*>(l.ln2), static_cast<const void*>(l.gateup_w), static_cast<const void*>(l.down_w),
+                            static_cast<const void*>(ctx->k_pool[i]), static_cast<const void*>(ctx->v_pool[i])})
+        tab.push_back(q);
+    }
+    if (ctx->d_layer_table == nullptr) {
+      const void** dt = nullptr;
+      if (dalloc(ctx, &dt, tab.size())) return 1;
+      ctx->d_layer_table = dt;
+    }
+    TB_CUDA(cudaMemcpy(ctx->d_layer_table, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  }
   TB_CUDA(cudaDeviceSynchronize());
   ctx->finalized = true;
   return 0;
@@ -617,7 +656,7 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
                       ctx->score_tab, ctx->sync_tab, c.hidden, ctx->st, ctx->d_x, 0, s));
   int done = 0;
   int steps_run = 1;
-  const int64_t per_step = static_cast<int64_t>(c.layers) * 5 + 2;
+  const int64_t per_step = ctx->fused_decode ? 1 : static_cast<int64_t>(c.layers) * 5 + 2;
   auto poll_done = [&]() -> int {
     TB_CUDA(cudaMemcpyAsync(&done, ctx->st.done_step, 4, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaStreamSynchronize(s));

@@ -85,4 +85,27 @@ int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, i
                     const __half* embed, const __half* time_tab, const __half* score_tab, const __half* sync_tab,
                     int H, const DecodeState& st, __half* x_next, int advance_pos, cudaStream_t stream);
 
+// ---- decode_mega.cu : the whole decode step as one persistent kernel -------------------------------------------
+struct DecodeMegaArgs {
+  int B, H, qkvw, qd, ffn, layers, heads, kvh, vocab, head_rows, n_valid, max_ctx, num_sms;
+  float eps;
+  const void* layer_table_dev;   // [layers] x {ln1, qkv_w, o_w, ln2, gateup_w, down_w, k_pool, v_pool} device pointers
+  const __half *final_norm, *head_w;
+  __half *x, *qkv, *attn, *act;
+  const float *cos_tab, *sin_tab;
+  const int32_t* block_table;
+  int max_pages, page_size;
+  float *part_o, *part_ml;
+  int32_t* counters;
+  float* cand_val;
+  int32_t* cand_idx;
+  float* logits_out;
+  const __half *embed, *time_tab, *score_tab, *sync_tab;
+  int eos, pad;
+  DecodeState st;
+  unsigned* gbar;                // [2] zero-initialised: grid barrier + exit counters
+};
+int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream);
+int decode_mega_layer_table_bytes();
+
 }  // namespace tb
