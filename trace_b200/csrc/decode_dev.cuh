@@ -111,29 +111,76 @@ __device__ __forceinline__ GvSmem gv_carve(uint8_t* smem, int B, int KP, int KS,
   return m;
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// Enumerates the (k-phase, tile, k-stage) items of one matrix for one CTA, skipping tiles without a needed row.
+struct GvItems {
+  int K, KP, KS, r0, ntile, vlo, vhi;
+  int k0, tile, ks;
+  bool done;
+  __device__ __forceinline__ void init(int K_, int KP_, int KS_, int r0_, int r1_, int vlo_, int vhi_) {
+    K = K_; KP = KP_; KS = KS_; r0 = r0_; vlo = vlo_; vhi = vhi_;
+    ntile = (r1_ - r0_ + GV_TILE - 1) / GV_TILE;
+    k0 = 0; tile = 0; ks = 0; done = false;
+    skip();
+  }
+  __device__ __forceinline__ bool tile_ok() const {
+    const int tr0 = r0 + tile * GV_TILE;
+    return max(tr0, vlo) < min(tr0 + GV_TILE, vhi);
+  }
+  __device__ __forceinline__ void skip() {      // move to the next tile that has a needed row
+    while (!done && !tile_ok()) {
+      ks = 0;
+      if (++tile == ntile) { tile = 0; k0 += KP; if (k0 >= K) done = true; }
+    }
+  }
+  __device__ __forceinline__ void next() {
+    ks += KS;
+    if (ks >= KP) {
+      ks = 0;
+      if (++tile == ntile) { tile = 0; k0 += KP; if (k0 >= K) { done = true; return; } }
+      skip();
+    }
+  }
+};
+
 // ---- producer warp: streams rows [vlo,vhi) of the tiles of [r0,r1) in (phase, tile, k-stage) order ----------
 // One bulk copy per valid row per stage (lanes 0..15 issue them in one instruction); the copies do not depend on
-// the previous kernel, so this warp never executes griddepcontrol.wait and runs up to `stages` stages ahead.
+// the previous kernel / phase, so this warp never waits for activations and runs up to `stages` stages ahead in
+// shared memory plus `pf_ahead` further stages ahead in L2 (cp.async.bulk.prefetch.L2): while the consumers sit in a
+// barrier the HBM pipe keeps draining the next rows into L2, and the ring refills from L2 when they resume.
 __device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
-                                              int vhi, const GvSmem& m, int stages, int& s, uint32_t& ph) {
+                                              int vhi, const GvSmem& m, int stages, int& s, uint32_t& ph, int pf_ahead = 0) {
   const int lane = threadIdx.x & 31;
-  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
   const int pitch = KS + WS_PAD;
-  for (int k0 = 0; k0 < K; k0 += KP) {
-    for (int tile = 0; tile < ntile; ++tile) {
-      const int tr0 = r0 + tile * GV_TILE;
-      const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
-      if (lo >= hi) continue;                      // no row of this tile is needed (head GEMV on a narrow head)
-      for (int ks = 0; ks < KP; ks += KS) {
-        mbar_wait(&m.empty[s], ph ^ 1);
-        if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
-        __syncwarp();
-        const int row = tr0 + lane;
-        if (lane < GV_TILE && row >= lo && row < hi)
-          bulk_g2s(m.ws + static_cast<size_t>(s) * m.ws_stride + static_cast<size_t>(lane) * pitch, W + static_cast<size_t>(row) * K + k0 + ks, KS * 2, &m.full[s]);
-        if (++s == stages) { s = 0; ph ^= 1; }
+  GvItems it, pf;
+  it.init(K, KP, KS, r0, r1, vlo, vhi);
+  pf = it;
+  int lead = 0;                                  // how many items the prefetch iterator is ahead of the copy iterator
+  while (!it.done) {
+    while (lead < stages + pf_ahead && !pf.done) {
+      if (lead >= stages) {                      // the first `stages` items go straight into the ring
+        const int row = r0 + pf.tile * GV_TILE + lane;
+        if (lane < GV_TILE && row >= vlo && row < vhi && row < r0 + (pf.tile + 1) * GV_TILE)
+          bulk_prefetch_l2(W + static_cast<size_t>(row) * K + pf.k0 + pf.ks, KS * 2);
       }
+      pf.next();
+      ++lead;
     }
+    const int tr0 = r0 + it.tile * GV_TILE;
+    const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
+    mbar_wait(&m.empty[s], ph ^ 1);
+    if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
+    __syncwarp();
+    const int row = tr0 + lane;
+    if (lane < GV_TILE && row >= lo && row < hi)
+      bulk_g2s(m.ws + static_cast<size_t>(s) * m.ws_stride + static_cast<size_t>(lane) * pitch,
+               W + static_cast<size_t>(row) * K + it.k0 + it.ks, KS * 2, &m.full[s]);
+    if (++s == stages) { s = 0; ph ^= 1; }
+    it.next();
+    --lead;
   }
 }
 

@@ -83,6 +83,7 @@ struct MegaParams {
   DecodeState st;
   unsigned *gbar, *gexit;
   int kp_qkv, ks_qkv, kp_o, ks_o, kp_gu, ks_gu, kp_dn, ks_dn, kp_hd, ks_hd;
+  int pf_ahead;                       // L2 prefetch distance of the weight stream, in stages
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
 };
 
@@ -393,21 +394,47 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     int s = 0;
     uint32_t ph = 0;
     int r0, r1;
+    // this CTA's attention work item (fixed for the step): prefetch its K/V rows into L2 while the QKV weights stream
+    const int items = p.B * p.kvh * p.nsplit;
+    const int my_it = blockIdx.x < items ? static_cast<int>(blockIdx.x) : -1;
+    int a_kv = 0, a_start = 0, a_end = 0;
+    const int32_t* a_table = nullptr;
+    if (my_it >= 0) {
+      const int split = my_it % p.nsplit, b = my_it / (p.nsplit * p.kvh);
+      a_kv = (my_it / p.nsplit) % p.kvh;
+      const int t = p.st.pos[b];
+      int chunk = (t + p.nsplit - 1) / p.nsplit;
+      chunk = (chunk + 31) & ~31;
+      a_start = split * chunk;
+      a_end = min(a_start + chunk, t);
+      a_table = p.block_table + static_cast<size_t>(p.st.slot_ids[b]) * p.max_pages;
+    }
     for (int l = 0; l < p.layers; ++l) {
       const MegaLayer L = p.L[l];
+      if (p.pf_ahead > 0 && my_it >= 0 && items <= static_cast<int>(gridDim.x)) {
+        // pages are contiguous per (page, kv head): [page_size][128] halves
+        for (int k = a_start + (threadIdx.x & 31) * p.page_size - (a_start % p.page_size); k < a_end; k += 32 * p.page_size) {
+          const int lo = max(k, a_start), hi = min(k + p.page_size, a_end);
+          if (lo < hi) {
+            const size_t off = ((static_cast<size_t>(a_table[lo / p.page_size]) * p.kvh + a_kv) * p.page_size + lo % p.page_size) * MG_HD;
+            bulk_prefetch_l2(L.k_pool + off, static_cast<uint32_t>(hi - lo) * MG_HD * 2);
+            bulk_prefetch_l2(L.v_pool + off, static_cast<uint32_t>(hi - lo) * MG_HD * 2);
+          }
+        }
+      }
       cta_rows(p.qkvw, r0, r1);
-      gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph);
+      gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
       cta_rows(p.H, r0, r1);
-      gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph);
+      gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
       cta_rows(2 * p.ffn, r0, r1);
-      gemv_producer(L.gateup_w, p.H, p.kp_gu, p.ks_gu, r0, r1, r0, r1, m, p.stages, s, ph);
+      gemv_producer(L.gateup_w, p.H, p.kp_gu, p.ks_gu, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
       cta_rows(p.H, r0, r1);
-      gemv_producer(L.down_w, p.ffn, p.kp_dn, p.ks_dn, r0, r1, r0, r1, m, p.stages, s, ph);
+      gemv_producer(L.down_w, p.ffn, p.kp_dn, p.ks_dn, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
     }
     // head: only the rows some batch row decodes from (heads[] was written by the previous step)
     cta_rows(p.head_rows, r0, r1);
     const int vlo = max(ulo, r0), vhi = min(uhi, r1);
-    if (vlo < vhi) gemv_producer(p.head_w, p.H, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.stages, s, ph);
+    if (vlo < vhi) gemv_producer(p.head_w, p.H, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.stages, s, ph, p.pf_ahead);
     return;
   }
 
@@ -579,6 +606,14 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.part_o = a.part_o; p.part_ml = a.part_ml; p.counters = a.counters; p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
   p.logits_out = a.logits_out; p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
+  {
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("TRACE_B200_PF_AHEAD");
+      pf = (e != nullptr && atoi(e) >= 0 && atoi(e) <= 64) ? atoi(e) : 8;
+    }
+    p.pf_ahead = pf;
+  }
   int kpks[10];
   size_t smem = 0;
   if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.max_tiles,
