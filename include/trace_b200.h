@@ -100,6 +100,10 @@ int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);
 /* device time (CUDA events on the engine's decode stream) and decoder passes of the last trace_b200_decode */
 int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps_out);
 
+/* debugging aid: %globaltimer stamps of the last fused decode step, [2 CTAs][layers][10 phase points] (needs
+ * TRACE_B200_MEGA_TIMING=1 in the environment when the context is created). */
+int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity);
+
 /* ---- single-kernel entry points (unit-parity tests and micro-benchmarks) --------------------------- */
 int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                        const void* bias, const void* residual, int ldr, int act, int swiglu, void* stream);

@@ -38,4 +38,11 @@ for i in range(a.warm + 1):
 torch.cuda.synchronize()
 ms, st = model.engine.last_decode_timing()
 print("ids", out.tolist()[0][:16])
+if os.environ.get("TRACE_B200_MEGA_TIMING"):
+    tl = model.engine.debug_timeline().double()
+    names = ["qkv", "sync1", "attn", "sync2", "o", "sync3", "gateup", "sync4", "down", "sync0(next)"]
+    for c in range(2):
+        d = tl[c, :, 1:] - tl[c, :, :-1]
+        nxt = torch.cat([tl[c, 1:, 0] - tl[c, :-1, 9], torch.zeros(1, dtype=torch.float64)])
+        print(f"cta{c}: " + " ".join(f"{n}={float(d[1:-1, i].mean()) / 1e3:.2f}us" for i, n in enumerate(names[:-1])) + f" sync0={float(nxt[1:-1].mean()) / 1e3:.2f}us layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()) / 1e3:.2f}us")
 print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f}")

@@ -83,6 +83,7 @@ struct MegaParams {
   DecodeState st;
   unsigned *gbar, *gexit;
   int kp_qkv, ks_qkv, kp_o, ks_o, kp_gu, ks_gu, kp_dn, ks_dn, kp_hd, ks_hd;
+  unsigned long long* dbg;            // optional timeline [2 CTAs][layers][10] of %globaltimer stamps
   int pf_ahead;                       // L2 prefetch distance of the weight stream, in stages
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
 };
@@ -142,6 +143,15 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   const int start = split * chunk;
   const int end = min(start + chunk, t);
   const int nloc = max(end - start, 0);
+  // the first 16 V rows of this warp are requested now, together with the K rows (one memory round trip for both)
+  uint2 vpre[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int j = warp + u * GV_WARPS;
+    const int key = start + (j < nloc ? j : 0);
+    const int page = table[key / page_size];
+    vpre[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
+  }
   // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
   for (int base = warp * 16; base < nloc; base += GV_WARPS * 16) {
     const int j = base + (lane >> 1);
@@ -202,7 +212,19 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   float o[MG_G][4];
 #pragma unroll
   for (int h = 0; h < MG_G; ++h) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
-  for (int j0 = warp; j0 < nloc; j0 += GV_WARPS * 8) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int j = warp + u * GV_WARPS;
+    if (j < nloc) {
+      const float2 v0 = unpack_half2(vpre[u].x), v1 = unpack_half2(vpre[u].y);
+#pragma unroll
+      for (int h = 0; h < MG_G; ++h) {
+        const float pr = sc[h * cpitch + j];
+        o[h][0] += pr * v0.x; o[h][1] += pr * v0.y; o[h][2] += pr * v1.x; o[h][3] += pr * v1.y;
+      }
+    }
+  }
+  for (int j0 = warp + 16 * GV_WARPS; j0 < nloc; j0 += GV_WARPS * 8) {
     uint2 vreg[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -342,6 +364,35 @@ __device__ __forceinline__ void finalize_step(const MegaParams& p, int ncand) {
   }
 }
 
+// Pull this CTA's K/V slice of layer L towards L2 while the other CTAs are still finishing the QKV phase: the cached
+// rows do not depend on this step's q/k/v, so their HBM latency is taken off the attention critical path.
+__device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLayer& L) {
+  const int items = p.B * p.kvh * p.nsplit;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int split = it % p.nsplit, kv = (it / p.nsplit) % p.kvh, b = it / (p.nsplit * p.kvh);
+    const int t = p.st.pos[b];
+    const int32_t* table = p.block_table + static_cast<size_t>(p.st.slot_ids[b]) * p.max_pages;
+    int chunk = (t + p.nsplit - 1) / p.nsplit;
+    chunk = (chunk + 31) & ~31;
+    const int start = split * chunk, end = min(start + chunk, t);
+    // one 128-byte line per thread per pass: 2 lines per key row (256 B), K then V
+    for (int i = threadIdx.x; i < (end - start) * 2; i += GV_CONS) {
+      const int key = start + (i >> 1);
+      const size_t off = ((static_cast<size_t>(table[key / p.page_size]) * p.kvh + kv) * p.page_size + key % p.page_size) * MG_HD + (i & 1) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(L.k_pool + off));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(L.v_pool + off));
+    }
+  }
+}
+
+__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
+  if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 10 + k] = t;
+  }
+}
+
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
 template <int PRO, int EPI>
 __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
@@ -445,8 +496,12 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   for (int l = 0; l < p.layers; ++l) {
     const MegaLayer L = p.L[l];
     if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
+    stamp(p, l, 0);
+    attn_prefetch(p, L);
     gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, L.ln1, s, ph);
+    stamp(p, l, 1);
     grid_sync(p.gbar, target);                                                // q, k, v complete
+    stamp(p, l, 2);
     {
       const int items = p.B * p.kvh * p.nsplit;
       for (int it = blockIdx.x; it < items; it += ncta) {
@@ -455,12 +510,19 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
         cons_sync();
       }
     }
+    stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
+    stamp(p, l, 4);
     gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, nullptr, s, ph);
+    stamp(p, l, 5);
     grid_sync(p.gbar, target);
+    stamp(p, l, 6);
     gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, L.ln2, s, ph);
+    stamp(p, l, 7);
     grid_sync(p.gbar, target);
+    stamp(p, l, 8);
     gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, nullptr, s, ph);
+    stamp(p, l, 9);
   }
   grid_sync(p.gbar, target);
   // ---- heads: final RMSNorm + logits of the active ranges + argmax candidates ----
@@ -610,10 +672,11 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
     static int pf = -1;
     if (pf < 0) {
       const char* e = getenv("TRACE_B200_PF_AHEAD");
-      pf = (e != nullptr && atoi(e) >= 0 && atoi(e) <= 64) ? atoi(e) : 8;
+      pf = (e != nullptr && atoi(e) >= 0 && atoi(e) <= 64) ? atoi(e) : 0;
     }
     p.pf_ahead = pf;
   }
+  p.dbg = a.dbg;
   int kpks[10];
   size_t smem = 0;
   if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.max_tiles,

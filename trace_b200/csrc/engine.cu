@@ -89,6 +89,7 @@ struct trace_b200_ctx {
   // fused decode step (decode_mega.cu)
   void* d_layer_table = nullptr;
   unsigned* d_gbar = nullptr;
+  unsigned long long* d_dbg = nullptr;
   bool fused_decode = true;
 };
 
@@ -224,6 +225,7 @@ int allocate_all(trace_b200_ctx* ctx) {
       dalloc(ctx, &ctx->st.slot_ids, kMaxB, true))
     return 1;
   if (dalloc(ctx, &ctx->d_gbar, 4, true)) return 1;
+  if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 10, true)) return 1;
   {
     const char* env = getenv("TRACE_B200_DECODE_PEROP");
     ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
@@ -424,7 +426,7 @@ int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out,
     a.block_table = ctx->d_block_table; a.max_pages = ctx->max_pages_seq; a.page_size = kPage; a.part_o = ctx->d_part_o;
     a.part_ml = ctx->d_part_ml; a.counters = ctx->d_counters; a.cand_val = ctx->d_cand_val; a.cand_idx = ctx->d_cand_idx;
     a.logits_out = logits_out; a.embed = ctx->embed; a.time_tab = ctx->time_tab; a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab;
-    a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar;
+    a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar; a.dbg = ctx->d_dbg;
     RUN(decode_step_fused(a, s));
     return 0;
   }
@@ -724,6 +726,14 @@ int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps
   return 0;
 }
 int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx) { return ctx ? ctx->weight_bytes : 0; }
+int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity) {
+  TB_CHECK(ctx != nullptr && out_host != nullptr, "null argument");
+  TB_CHECK(ctx->d_dbg != nullptr, "timeline not enabled (set TRACE_B200_MEGA_TIMING=1 before creating the context)");
+  const int n = 2 * ctx->c.layers * 10;
+  TB_CHECK(capacity >= n, "timeline buffer too small");
+  TB_CUDA(cudaMemcpy(out_host, ctx->d_dbg, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 // ---- single-kernel entry points -----------------------------------------------------------------
 static int sm_count() {

@@ -104,6 +104,7 @@ struct DecodeMegaArgs {
   int eos, pad;
   DecodeState st;
   unsigned* gbar;                // [2] zero-initialised: grid barrier + exit counters
+  unsigned long long* dbg;       // optional timeline buffer [2][layers][10] (nullptr = off)
 };
 int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream);
 int decode_mega_layer_table_bytes();

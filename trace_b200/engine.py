@@ -21,7 +21,7 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
     "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_gemv",
 ]
 
@@ -69,6 +69,7 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_launch_count.argtypes = [vp]
     lib.trace_b200_launch_count.restype = i64
     lib.trace_b200_last_decode_timing.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
+    lib.trace_b200_debug_timeline.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), i32]
     lib.trace_b200_weight_bytes.argtypes = [vp]
     lib.trace_b200_weight_bytes.restype = i64
     lib.trace_b200_op_gemm.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp]
@@ -216,6 +217,12 @@ class Engine:
         ms, st = ctypes.c_float(0), ctypes.c_int(0)
         _check(self.lib.trace_b200_last_decode_timing(self._h, ctypes.byref(ms), ctypes.byref(st)))
         return ms.value, st.value
+
+    def debug_timeline(self):
+        n = 2 * self.dims.layers * 10
+        buf = (ctypes.c_uint64 * n)()
+        _check(self.lib.trace_b200_debug_timeline(self._h, buf, n))
+        return torch.tensor(list(buf), dtype=torch.int64).view(2, self.dims.layers, 10)
 
     @property
     def weight_bytes(self) -> int:
