@@ -18,6 +18,19 @@ ap.add_argument("--max-new", type=int, default=4)
 ap.add_argument("--warm", type=int, default=0)
 ap.add_argument("--batch", type=int, default=1)
 a = ap.parse_args()
+def box_hbm_gbs():
+    x = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    y = torch.empty_like(x)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); y.copy_(x); e1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * x.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del x, y
+    return best
+
+
+BOX_GBS = box_hbm_gbs()
 d = synth.full_dims(a.frames)
 S = 14 * a.frames + L_TEXT - 1
 model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frames=32, max_prefill_tokens=S * a.batch,
@@ -45,4 +58,4 @@ if os.environ.get("TRACE_B200_MEGA_TIMING"):
         d = tl[c, :, 1:] - tl[c, :, :-1]
         nxt = torch.cat([tl[c, 1:, 0] - tl[c, :-1, 9], torch.zeros(1, dtype=torch.float64)])
         print(f"cta{c}: " + " ".join(f"{n}={float(d[1:-1, i].mean()) / 1e3:.2f}us" for i, n in enumerate(names[:-1])) + f" sync0={float(nxt[1:-1].mean()) / 1e3:.2f}us layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()) / 1e3:.2f}us")
-print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f}")
+print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f} box_copy_GBs={BOX_GBS:.0f} floor_ms_at_box_bw={14.0e9 / BOX_GBS / 1e6:.3f}")
