@@ -97,6 +97,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   float* vnew = knew + MG_HD;                    // [128]
   float* red = vnew + MG_HD;                     // [8 warps][4][128]
   float* sc = red + GV_WARPS * MG_G * MG_HD;     // [4][chunk_max + 1]
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int heads = p.heads, kvh = p.kvh, nsplit = p.nsplit, page_size = p.page_size;
   const int t = p.st.pos[b];
@@ -271,6 +272,36 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2, mx);
     __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2 + 1, l);
   }
+  __threadfence();
+  cons_sync();
+  if (tid == 0) s_last = (atomicAdd(&p.counters[b * kvh + kv], 1) == nsplit - 1);
+  cons_sync();
+  if (s_last) {     // the last split of this (row, kv head) combines the partials -> attn [B, heads*128] fp16
+    __threadfence();
+    if (tid < 128) {
+      const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
+      const int h = tid >> 5;
+      float M = -INFINITY;
+      for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2));
+      float Lsum = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < nsplit; ++s) {
+        const float ms = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2);
+        const float ls = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2 + 1);
+        if (ls == 0.f) continue;
+        const float w = __expf(ms - M);
+        Lsum += w * ls;
+        const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + s) * (MG_G * MG_HD) + tid * 4));
+        acc.x += w * po.x; acc.y += w * po.y; acc.z += w * po.z; acc.w += w * po.w;
+      }
+      const float inv = 1.f / Lsum;
+      uint2 pk;
+      pk.x = pack_half2(acc.x * inv, acc.y * inv);
+      pk.y = pack_half2(acc.z * inv, acc.w * inv);
+      __stcg(reinterpret_cast<uint2*>(p.attn + static_cast<size_t>(b) * heads * MG_HD + (kv * MG_G) * MG_HD + tid * 4), pk);
+    }
+    if (tid == 0) p.counters[b * kvh + kv] = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,37 +393,6 @@ __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
   }
 }
 
-// Activation staging of the O projection: merge the split-KV partials (running-max / sum form) of every head straight
-// into the staged fp16 vector -- every CTA rebuilds the full [B, heads*128] attention output from L2 (nsplit x 16.6 KB
-// per row), which removes the atomic + fence + "last CTA combines" tail from the attention phase.
-__device__ __forceinline__ void stage_attn_combine(const MegaParams& p, __half* xs, int KP) {
-  const int pitch = KP + XS_PAD;
-  const int qd = p.qd, nsplit = p.nsplit;
-  for (int b = 0; b < p.B; ++b) {
-    for (int o4 = threadIdx.x; o4 < qd / 4; o4 += GV_CONS) {      // 4 consecutive dims of one head
-      const int head = (o4 * 4) / MG_HD, kv = head / MG_G, h = head % MG_G, d = (o4 * 4) % MG_HD;
-      const size_t gb = (static_cast<size_t>(b) * p.kvh + kv) * nsplit;
-      float M = -INFINITY;
-      for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2));
-      float Lsum = 0.f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < nsplit; ++s) {
-        const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (gb + s) * (MG_G * 2) + h * 2));
-        if (ml.y == 0.f) continue;
-        const float w = __expf(ml.x - M);
-        Lsum += w * ml.y;
-        const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + s) * (MG_G * MG_HD) + h * MG_HD + d));
-        acc.x += w * po.x; acc.y += w * po.y; acc.z += w * po.z; acc.w += w * po.w;
-      }
-      const float inv = 1.f / Lsum;
-      uint2 pk;
-      pk.x = pack_half2(acc.x * inv, acc.y * inv);
-      pk.y = pack_half2(acc.z * inv, acc.w * inv);
-      *reinterpret_cast<uint2*>(xs + b * pitch + o4 * 4) = pk;
-    }
-  }
-}
-
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
 template <int PRO, int EPI>
 __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
@@ -401,8 +401,7 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
   cta_rows(N, r0, r1);
   for (int k0 = 0; k0 < K; k0 += KP) {
     if (k0 > 0) cons_sync();
-    if (PRO == 2) stage_attn_combine(p, m.xs, KP);
-    else stage_x<PRO>(m.xs, xin, ldx, p.B, k0, KP, K, gamma, p.eps, m.s_red);
+    stage_x<PRO>(m.xs, xin, ldx, p.B, k0, KP, K, gamma, p.eps, m.s_red);
     cons_sync();
     // the staged row pitch is KP + XS_PAD: gemv_consume_phase derives it from KP
     gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages, s, ph);
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
     stamp(p, l, 4);
-    gemv_phase_cons<2, 1>(p, m, nullptr, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, nullptr, s, ph);
+    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, nullptr, s, ph);
     stamp(p, l, 5);
     grid_sync(p.gbar, target);
     stamp(p, l, 6);
@@ -623,7 +622,7 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   for (int i = 0; i < 5; ++i) {
     int kp = pick_kp_cap(Ks[i], B, xcap);
     TB_CHECK(kp > 0, "decode GEMV K must be a multiple of 256");
-    if (i != 3) TB_CHECK(kp == Ks[i], "RMSNorm / attention-merge staging needs the whole input row staged");
+    if (i == 0 || i == 2 || i == 4) TB_CHECK(kp == Ks[i], "fused RMSNorm needs the whole hidden row staged");
     kp_ks[2 * i] = kp;
     kp_ks[2 * i + 1] = pick_ks2(kp);
     if (kp > kpmax) kpmax = kp;
@@ -636,12 +635,8 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
     if (t > max_tiles) max_tiles = t;
   }
   int nsplit = num_sms / (B * kvh);
-  if (nsplit > 8) nsplit = 8;        // partials are merged by every CTA while it stages the O projection: keep them few
-  {
-    const char* e = getenv("TRACE_B200_ATTN_SPLITS");
-    if (e != nullptr && atoi(e) >= 1 && atoi(e) <= 32) nsplit = atoi(e);
-  }
   if (nsplit < 1) nsplit = 1;
+  if (nsplit > 32) nsplit = 32;
   const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
   // attention scratch lives in the s_part region: qs + knew + vnew + red + sc
   const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + static_cast<size_t>(MG_G) * (chunk_max + 1)) * 4;
