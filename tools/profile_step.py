@@ -52,10 +52,13 @@ torch.cuda.synchronize()
 ms, st = model.engine.last_decode_timing()
 print("ids", out.tolist()[0][:16])
 if os.environ.get("TRACE_B200_MEGA_TIMING"):
-    tl = model.engine.debug_timeline().double()
-    names = ["qkv", "sync1", "attn", "sync2", "o", "sync3", "gateup", "sync4", "down", "sync0(next)"]
+    tl = model.engine.debug_timeline().double() / 1e3   # us
+    names = ["qkv", "sync1", "attn", "sync2", "o", "sync3", "gateup", "sync4", "down"]
     for c in range(2):
-        d = tl[c, :, 1:] - tl[c, :, :-1]
-        nxt = torch.cat([tl[c, 1:, 0] - tl[c, :-1, 9], torch.zeros(1, dtype=torch.float64)])
-        print(f"cta{c}: " + " ".join(f"{n}={float(d[1:-1, i].mean()) / 1e3:.2f}us" for i, n in enumerate(names[:-1])) + f" sync0={float(nxt[1:-1].mean()) / 1e3:.2f}us layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()) / 1e3:.2f}us")
+        x = tl[c, 1:-1]
+        d = x[:, 1:10] - x[:, 0:9]
+        nxt = tl[c, 2:, 0] - tl[c, 1:-1, 9]
+        print(f"cta{c}: " + " ".join(f"{n}={float(d[:, i].mean()):.2f}" for i, n in enumerate(names)) + f" sync0={float(nxt.mean()):.2f} layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()):.2f} us")
+        for nm, st0, k in (("qkv", 0, 10), ("o", 4, 12), ("gateup", 6, 14), ("down", 8, 16)):
+            print(f"   {nm}: stage_x={float((x[:, k] - x[:, st0]).mean()):.2f} consume={float((x[:, k + 1] - x[:, k]).mean()):.2f} epilogue={float((x[:, st0 + 1] - x[:, k + 1]).mean()):.2f}")
 print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f} box_copy_GBs={BOX_GBS:.0f} floor_ms_at_box_bw={14.0e9 / BOX_GBS / 1e6:.3f}")

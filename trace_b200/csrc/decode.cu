@@ -38,12 +38,15 @@ gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx,
     gemv_producer(W, K, KP, KS, r0, r1, r0, r1, m, stages, ps, pph);    // weights never depend on the previous kernel
     return;
   }
-  pdl_wait();                                                  // activations do
+  GammaRegs gm;
+  if (PRO == 1) gm = load_gamma(gamma, K);                     // a weight: fetched before the dependency wait
+  pdl_wait();                                                  // activations do depend on the previous kernel
   int s = 0;
   uint32_t ph = 0;
   for (int k0 = 0; k0 < K; k0 += KP) {
     if (k0 > 0) cons_sync();
-    stage_x<PRO>(m.xs, x, ldx, B, k0, KP, K, gamma, eps, m.s_red);
+    if (PRO == 1) stage_x_rmsnorm(m.xs, x, ldx, B, K, gm, eps, m.s_red);
+    else stage_x_plain(m.xs, x, ldx, B, k0, KP);
     cons_sync();
     gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, B, stages, s, ph);
   }
@@ -172,7 +175,8 @@ head_gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int
   int bi = 0x7fffffff;
   const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
   if (vlo < vhi) {
-    stage_x<1>(m.xs, x, ldx, B, 0, K, K, gamma, eps, m.s_red);
+    const GammaRegs gm = load_gamma(gamma, K);
+    stage_x_rmsnorm(m.xs, x, ldx, B, K, gm, eps, m.s_red);
     cons_sync();
     int s = 0;
     uint32_t ph = 0;

@@ -33,59 +33,99 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- activation staging (+ optional RMSNorm) into shared memory: xs[b][k], b < B, k in [k0, k0+KP) ----
-// executed by the 256 consumer threads only
-template <int PRO>
-__device__ __forceinline__ void stage_x(__half* xs, const __half* x, int ldx, int B, int k0, int KP, int K,
-                                        const __half* gamma, float eps, float* s_red) {
-  const int tid = threadIdx.x;
+// ---- activation staging into shared memory: xs[b][k], b < B, k in [k0, k0+KP) --------------------------------
+// executed by the 256 consumer threads only.  Activations are read with ld.global.cg (other CTAs rewrite them
+// between the phases of the fused decode step).
+__device__ __forceinline__ void stage_x_plain(__half* xs, const __half* x, int ldx, int B, int k0, int KP) {
   const int pitch = KP + XS_PAD;
-  if (PRO == 1) {
-    // HF MistralRMSNorm: fp32 mean of squares over the full row (KP == K)
-    float ss[GV_MAXB];
+  for (int b = 0; b < B; ++b)
+    for (int i = threadIdx.x; i < KP / 8; i += GV_CONS)
+      *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8));
+}
+
+// RMSNorm weights of this thread's columns: a weight, so it can be fetched BEFORE the activations exist (before the
+// grid barrier / griddepcontrol.wait) and its HBM latency disappears from the critical path.
+struct GammaRegs { uint4 g[2]; };
+__device__ __forceinline__ GammaRegs load_gamma(const __half* gamma, int K) {
+  GammaRegs r;
 #pragma unroll
-    for (int b = 0; b < GV_MAXB; ++b) {
-      ss[b] = 0.f;
-      if (b < B) {
-        for (int i = tid; i < K / 8; i += GV_CONS) {
-          uint4 u = __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + i * 8));
-          float2 a = unpack_half2(u.x), c = unpack_half2(u.y), d = unpack_half2(u.z), e = unpack_half2(u.w);
-          ss[b] += a.x * a.x + a.y * a.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y + e.x * e.x + e.y * e.y;
-        }
-        ss[b] = warp_sum(ss[b]);
+  for (int j = 0; j < 2; ++j) {
+    const int i = threadIdx.x + j * GV_CONS;
+    r.g[j] = (i < K / 8) ? *reinterpret_cast<const uint4*>(gamma + i * 8) : make_uint4(0, 0, 0, 0);
+  }
+  return r;
+}
+
+// HF MistralRMSNorm (fp32 mean of squares over the full row, x*rstd rounded to fp16, then weight * that in fp16)
+// fused into the staging: ONE read of x (kept in registers across the reduction), one barrier pair.  K <= 4096.
+template <int NB>
+__device__ __forceinline__ void stage_x_rmsnorm_nb(__half* xs, const __half* x, int ldx, int B, int K, const GammaRegs& gm, float eps,
+                                                   float* s_red) {
+  const int tid = threadIdx.x;
+  const int pitch = K + XS_PAD;
+  uint4 xr[NB][2];
+  float ss[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    ss[b] = 0.f;
+    if (b < B) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * GV_CONS;
+        xr[b][j] = (i < K / 8) ? __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + i * 8)) : make_uint4(0, 0, 0, 0);
       }
     }
-    const int w = tid >> 5, l = tid & 31;
-    if (l == 0)
+  }
 #pragma unroll
-      for (int b = 0; b < GV_MAXB; ++b) s_red[w * GV_MAXB + b] = ss[b];
-    cons_sync();
-    if (tid < GV_MAXB) {
+  for (int b = 0; b < NB; ++b) {
+    if (b < B) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint4 u = xr[b][j];
+        float2 a = unpack_half2(u.x), c = unpack_half2(u.y), d = unpack_half2(u.z), e = unpack_half2(u.w);
+        ss[b] += a.x * a.x + a.y * a.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y + e.x * e.x + e.y * e.y;
+      }
+      ss[b] = warp_sum(ss[b]);
+    }
+  }
+  const int w = tid >> 5, l = tid & 31;
+  if (l == 0)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) s_red[w * GV_MAXB + b] = ss[b];
+  cons_sync();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b < B) {
       float t = 0.f;
-      for (int i = 0; i < GV_WARPS; ++i) t += s_red[i * GV_MAXB + tid];
-      s_red[GV_WARPS * GV_MAXB + tid] = rsqrtf(t / K + eps);
-    }
-    cons_sync();
-  }
-  for (int b = 0; b < B; ++b) {
-    const float rstd = (PRO == 1) ? s_red[GV_WARPS * GV_MAXB + b] : 1.f;
-    for (int i = tid; i < KP / 8; i += GV_CONS) {
-      uint4 u = __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8));
-      if (PRO == 1) {
-        uint4 gm = *reinterpret_cast<const uint4*>(gamma + k0 + i * 8);
-        uint32_t* up = &u.x;
-        const uint32_t* gp = &gm.x;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 v = unpack_half2(up[j]);
-          float2 gg = unpack_half2(gp[j]);
-          // weight * (x*rstd).to(fp16) : two roundings as in the reference
-          up[j] = pack_half2(gg.x * __half2float(__float2half_rn(v.x * rstd)), gg.y * __half2float(__float2half_rn(v.y * rstd)));
+      for (int i = 0; i < GV_WARPS; ++i) t += s_red[i * GV_MAXB + b];     // same order in every thread: deterministic
+      const float rstd = rsqrtf(t / K + eps);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * GV_CONS;
+        if (i < K / 8) {
+          uint4 u = xr[b][j];
+          uint32_t* up = &u.x;
+          const uint32_t* gp = &gm.g[j].x;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 v = unpack_half2(up[q]);
+            float2 gg = unpack_half2(gp[q]);
+            up[q] = pack_half2(gg.x * __half2float(__float2half_rn(v.x * rstd)), gg.y * __half2float(__float2half_rn(v.y * rstd)));
+          }
+          *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = u;
         }
       }
-      *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = u;
     }
   }
+}
+
+__device__ __forceinline__ void stage_x_rmsnorm(__half* xs, const __half* x, int ldx, int B, int K, const GammaRegs& gm, float eps,
+                                                float* s_red) {
+  if (B == 1) stage_x_rmsnorm_nb<1>(xs, x, ldx, B, K, gm, eps, s_red);        // keeps the common case free of spills
+  else if (B <= 2) stage_x_rmsnorm_nb<2>(xs, x, ldx, B, K, gm, eps, s_red);
+  else if (B <= 4) stage_x_rmsnorm_nb<4>(xs, x, ldx, B, K, gm, eps, s_red);
+  else stage_x_rmsnorm_nb<8>(xs, x, ldx, B, K, gm, eps, s_red);
 }
 
 // Shared-memory carve-up of a GEMV CTA.

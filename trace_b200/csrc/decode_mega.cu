@@ -389,24 +389,28 @@ __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
   if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 10 + k] = t;
+    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 20 + k] = t;
   }
 }
 
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
 template <int PRO, int EPI>
 __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
-                                                int N, int K, int KP, int KS, const __half* gamma, int& s, uint32_t& ph) {
+                                                int N, int K, int KP, int KS, const GammaRegs& gm, int& s, uint32_t& ph,
+                                                int dl = 0, int dk = -1) {
   int r0, r1;
   cta_rows(N, r0, r1);
   for (int k0 = 0; k0 < K; k0 += KP) {
     if (k0 > 0) cons_sync();
-    stage_x<PRO>(m.xs, xin, ldx, p.B, k0, KP, K, gamma, p.eps, m.s_red);
+    if (PRO == 1) stage_x_rmsnorm(m.xs, xin, ldx, p.B, K, gm, p.eps, m.s_red);
+    else stage_x_plain(m.xs, xin, ldx, p.B, k0, KP);
     cons_sync();
+    if (dk >= 0 && k0 == 0) stamp(p, dl, dk);
     // the staged row pitch is KP + XS_PAD: gemv_consume_phase derives it from KP
     gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages, s, ph);
   }
   cons_sync();
+  if (dk >= 0) stamp(p, dl, dk + 1);
   gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
 }
 
@@ -495,10 +499,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   uint32_t ph = 0;
   for (int l = 0; l < p.layers; ++l) {
     const MegaLayer L = p.L[l];
+    GammaRegs gm = load_gamma(L.ln1, p.H);                                    // weights: issued before the barrier
+    attn_prefetch(p, L);
     if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
     stamp(p, l, 0);
-    attn_prefetch(p, L);
-    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, L.ln1, s, ph);
+    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
     stamp(p, l, 1);
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
@@ -513,17 +518,19 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
     stamp(p, l, 4);
-    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, nullptr, s, ph);
+    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, s, ph, l, 12);
     stamp(p, l, 5);
+    gm = load_gamma(L.ln2, p.H);
     grid_sync(p.gbar, target);
     stamp(p, l, 6);
-    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, L.ln2, s, ph);
+    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, s, ph, l, 14);
     stamp(p, l, 7);
     grid_sync(p.gbar, target);
     stamp(p, l, 8);
-    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, nullptr, s, ph);
+    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, s, ph, l, 16);
     stamp(p, l, 9);
   }
+  const GammaRegs gmf = load_gamma(p.final_norm, p.H);
   grid_sync(p.gbar, target);
   // ---- heads: final RMSNorm + logits of the active ranges + argmax candidates ----
   {
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     __shared__ float s_cv[GV_WARPS][8];
     __shared__ int s_ci[GV_WARPS][8];
     if (vlo < vhi) {
-      stage_x<1>(m.xs, p.x, p.H, p.B, 0, p.kp_hd, p.H, p.final_norm, p.eps, m.s_red);
+      stage_x_rmsnorm(m.xs, p.x, p.H, p.B, p.H, gmf, p.eps, m.s_red);
       cons_sync();
       gemv_consume_phase(0, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.B, p.stages, s, ph);
       cons_sync();
