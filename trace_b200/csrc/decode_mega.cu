@@ -32,10 +32,10 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
   cons_sync();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // release-reduction: orders every write this CTA made before the bar.sync above (cumulativity) without a separate
+    // membar.gl + atomic round trip; the acquire loads below pair with it
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     while (ld_acquire_u32(bar) < target) { }
-    __threadfence();
   }
   cons_sync();
 }
@@ -281,18 +281,34 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     if (tid < 128) {
       const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
       const int h = tid >> 5;
+      // all partial statistics first (independent loads -> one L2 round trip), then all partial outputs
+      float2 ml[32];
+#pragma unroll
+      for (int s = 0; s < 32; ++s)
+        ml[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float2*>(p.part_ml + (gb + s) * (MG_G * 2) + h * 2)) : make_float2(-INFINITY, 0.f);
       float M = -INFINITY;
-      for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2));
+#pragma unroll
+      for (int s = 0; s < 32; ++s) M = fmaxf(M, ml[s].x);
       float Lsum = 0.f;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < nsplit; ++s) {
-        const float ms = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2);
-        const float ls = __ldcg(p.part_ml + (gb + s) * (MG_G * 2) + h * 2 + 1);
-        if (ls == 0.f) continue;
-        const float w = __expf(ms - M);
-        Lsum += w * ls;
-        const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + s) * (MG_G * MG_HD) + tid * 4));
-        acc.x += w * po.x; acc.y += w * po.y; acc.z += w * po.z; acc.w += w * po.w;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half * 16 < nsplit) {
+          float4 po[16];
+#pragma unroll
+          for (int s = 0; s < 16; ++s)
+            po[s] = (half * 16 + s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + half * 16 + s) * (MG_G * MG_HD) + tid * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < 16; ++s) {
+            const float2 m2 = ml[half * 16 + s];
+            if (half * 16 + s < nsplit && m2.y != 0.f) {
+              const float w = __expf(m2.x - M);
+              Lsum += w * m2.y;
+              acc.x += w * po[s].x; acc.y += w * po[s].y; acc.z += w * po[s].z; acc.w += w * po[s].w;
+            }
+          }
+        }
       }
       const float inv = 1.f / Lsum;
       uint2 pk;
@@ -414,7 +430,7 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
   gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
 }
 
-__global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __maxnreg__(224) decode_step_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve with the largest stage (KS = 1024) and the reserved activation capacity
   GvSmem m;
