@@ -430,7 +430,7 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
   gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
 }
 
-__global__ void __maxnreg__(224) decode_step_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve with the largest stage (KS = 1024) and the reserved activation capacity
   GvSmem m;
