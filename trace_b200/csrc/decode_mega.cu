@@ -88,10 +88,47 @@ struct MegaParams {
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
 };
 
+// Per-step attention control block of this CTA's (fixed) work item: everything that would otherwise be a chain of
+// dependent global loads inside every layer's attention phase (pos -> slot -> block table -> row address; RoPE row).
+struct AttnCtl {
+  int valid, b, kv, split, t, start, end, page_new;
+  int pages[64];            // page id of key range page i (i = key/page_size - start/page_size)
+  float cs[MG_HD / 2], sn[MG_HD / 2];
+};
+__device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
+  const int items = p.B * p.kvh * p.nsplit;
+  const int it = blockIdx.x;
+  if (threadIdx.x == 0) {
+    c->valid = it < items;
+    if (it < items) {
+      c->split = it % p.nsplit; c->kv = (it / p.nsplit) % p.kvh; c->b = it / (p.nsplit * p.kvh);
+      c->t = p.st.pos[c->b];
+      int chunk = (c->t + p.nsplit - 1) / p.nsplit;
+      chunk = (chunk + 31) & ~31;
+      c->start = c->split * chunk;
+      c->end = min(c->start + chunk, c->t);
+    }
+  }
+  cons_sync();
+  if (c->valid) {
+    const int32_t* table = p.block_table + static_cast<size_t>(p.st.slot_ids[c->b]) * p.max_pages;
+    const int p0 = c->start / p.page_size;
+    const int np = (c->end > c->start) ? (c->end - 1) / p.page_size - p0 + 1 : 0;
+    for (int i = threadIdx.x; i < np && i < 64; i += GV_CONS) c->pages[i] = table[p0 + i];
+    if (threadIdx.x == 64) c->page_new = table[c->t / p.page_size];
+    if (threadIdx.x < MG_HD / 2) {
+      c->cs[threadIdx.x] = p.cos_tab[static_cast<size_t>(c->t) * (MG_HD / 2) + threadIdx.x];
+      c->sn[threadIdx.x] = p.sin_tab[static_cast<size_t>(c->t) * (MG_HD / 2) + threadIdx.x];
+    }
+  }
+  cons_sync();
+}
+
 // ------------------------------------------------------------------------------------------------
 // attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, int b, int kv, int split, float* scratch) {
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch) {
+  const int b = ctl.b, kv = ctl.kv, split = ctl.split;
   float* qs = scratch;                           // [4][128]
   float* knew = qs + MG_G * MG_HD;               // [128]
   float* vnew = knew + MG_HD;                    // [128]
@@ -100,14 +137,13 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int heads = p.heads, kvh = p.kvh, nsplit = p.nsplit, page_size = p.page_size;
-  const int t = p.st.pos[b];
-  const int slot = p.st.slot_ids[b];
-  const int32_t* table = p.block_table + static_cast<size_t>(slot) * p.max_pages;
+  const int t = ctl.t;
+  const int pg0 = ctl.start / page_size;
   const __half* row = p.qkv + static_cast<size_t>(b) * p.qkvw;
   const float scale = rsqrtf(static_cast<float>(MG_HD));
   const int cpitch = p.chunk_max + 1;
-  const float* cs = p.cos_tab + static_cast<size_t>(t) * (MG_HD / 2);
-  const float* sn = p.sin_tab + static_cast<size_t>(t) * (MG_HD / 2);
+  const float* cs = ctl.cs;
+  const float* sn = ctl.sn;
   for (int i = tid; i < MG_G * (MG_HD / 2); i += GV_CONS) {
     const int h = i / (MG_HD / 2), d = i % (MG_HD / 2);
     const __half* qp = row + (kv * MG_G + h) * MG_HD;
@@ -116,7 +152,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     qs[h * MG_HD + d + MG_HD / 2] = __half2float(__float2half_rn(c2 * cs[d] + a * sn[d])) * scale;
   }
   if (split == 0) {
-    const int page = table[t / page_size], poff = t % page_size;
+    const int page = ctl.page_new, poff = t % page_size;
     const size_t dst = ((static_cast<size_t>(page) * kvh + kv) * page_size + poff) * MG_HD;
     if (tid < MG_HD / 2) {
       const __half* kp = row + (heads + kv) * MG_HD;
@@ -138,10 +174,8 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     }
   }
   cons_sync();
-  int chunk = (t + nsplit - 1) / nsplit;
-  chunk = (chunk + 31) & ~31;
-  const int start = split * chunk;
-  const int end = min(start + chunk, t);
+  const int start = ctl.start;
+  const int end = ctl.end;
   const int nloc = max(end - start, 0);
   // the first 16 V rows of this warp are requested now, together with the K rows (one memory round trip for both)
   uint2 vpre[16];
@@ -149,7 +183,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   for (int u = 0; u < 16; ++u) {
     const int j = warp + u * GV_WARPS;
     const int key = start + (j < nloc ? j : 0);
-    const int page = table[key / page_size];
+    const int page = ctl.pages[key / page_size - pg0];
     vpre[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
   }
   // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
@@ -158,7 +192,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     const int hf = lane & 1;
     const bool valid = j < nloc;
     const int key = start + (valid ? j : 0);
-    const int page = table[key / page_size];
+    const int page = ctl.pages[key / page_size - pg0];
     const __half* kr = L.k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
     uint4 kreg[8];
 #pragma unroll
@@ -230,7 +264,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     for (int u = 0; u < 8; ++u) {
       const int j = j0 + u * GV_WARPS;
       const int key = start + (j < nloc ? j : 0);
-      const int page = table[key / page_size];
+      const int page = ctl.pages[key / page_size - pg0];
       vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
     }
 #pragma unroll
@@ -272,12 +306,14 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2, mx);
     __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2 + 1, l);
   }
-  __threadfence();
   cons_sync();
-  if (tid == 0) s_last = (atomicAdd(&p.counters[b * kvh + kv], 1) == nsplit - 1);
+  if (tid == 0) {   // acq_rel: releases this CTA's partials (cumulative over the bar.sync) and acquires the others'
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(p.counters + b * kvh + kv) : "memory");
+    s_last = (old == nsplit - 1);
+  }
   cons_sync();
   if (s_last) {     // the last split of this (row, kv head) combines the partials -> attn [B, heads*128] fp16
-    __threadfence();
     if (tid < 128) {
       const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
       const int h = tid >> 5;
@@ -382,22 +418,15 @@ __device__ __forceinline__ void finalize_step(const MegaParams& p, int ncand) {
 
 // Pull this CTA's K/V slice of layer L towards L2 while the other CTAs are still finishing the QKV phase: the cached
 // rows do not depend on this step's q/k/v, so their HBM latency is taken off the attention critical path.
-__device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLayer& L) {
-  const int items = p.B * p.kvh * p.nsplit;
-  for (int it = blockIdx.x; it < items; it += gridDim.x) {
-    const int split = it % p.nsplit, kv = (it / p.nsplit) % p.kvh, b = it / (p.nsplit * p.kvh);
-    const int t = p.st.pos[b];
-    const int32_t* table = p.block_table + static_cast<size_t>(p.st.slot_ids[b]) * p.max_pages;
-    int chunk = (t + p.nsplit - 1) / p.nsplit;
-    chunk = (chunk + 31) & ~31;
-    const int start = split * chunk, end = min(start + chunk, t);
-    // one 128-byte line per thread per pass: 2 lines per key row (256 B), K then V
-    for (int i = threadIdx.x; i < (end - start) * 2; i += GV_CONS) {
-      const int key = start + (i >> 1);
-      const size_t off = ((static_cast<size_t>(table[key / p.page_size]) * p.kvh + kv) * p.page_size + key % p.page_size) * MG_HD + (i & 1) * 64;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(L.k_pool + off));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(L.v_pool + off));
-    }
+__device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLayer& L, const AttnCtl& c) {
+  if (!c.valid) return;
+  const int pg0 = c.start / p.page_size;
+  // one 128-byte line per thread per pass: 2 lines per key row (256 B), K then V
+  for (int i = threadIdx.x; i < (c.end - c.start) * 2; i += GV_CONS) {
+    const int key = c.start + (i >> 1);
+    const size_t off = ((static_cast<size_t>(c.pages[key / p.page_size - pg0]) * p.kvh + c.kv) * p.page_size + key % p.page_size) * MG_HD + (i & 1) * 64;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(L.k_pool + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(L.v_pool + off));
   }
 }
 
@@ -510,13 +539,16 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   }
 
   // ===================== consumer warps =====================
+  __shared__ AttnCtl s_ctl;
+  AttnCtl* ctl = &s_ctl;
+  attn_ctl_init(p, ctl);
   unsigned target = 0;
   int s = 0;
   uint32_t ph = 0;
   for (int l = 0; l < p.layers; ++l) {
     const MegaLayer L = p.L[l];
     GammaRegs gm = load_gamma(L.ln1, p.H);                                    // weights: issued before the barrier
-    attn_prefetch(p, L);
+    attn_prefetch(p, L, *ctl);
     if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
     stamp(p, l, 0);
     gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
@@ -524,12 +556,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
     {
-      const int items = p.B * p.kvh * p.nsplit;
-      for (int it = blockIdx.x; it < items; it += ncta) {
-        const int split = it % p.nsplit, kv = (it / p.nsplit) % p.kvh, b = it / (p.nsplit * p.kvh);
-        attn_item(p, L, b, kv, split, m.s_part);
-        cons_sync();
-      }
+      if (ctl->valid) attn_item(p, L, *ctl, m.s_part);
     }
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
@@ -660,6 +687,8 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   int nsplit = num_sms / (B * kvh);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 32) nsplit = 32;
+  TB_CHECK(B * kvh * nsplit <= num_sms, "one attention work item per CTA");
+  TB_CHECK((max_ctx + nsplit - 1) / nsplit <= 62 * 64, "attention chunk exceeds the per-CTA page table (64 pages)");
   const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
   // attention scratch lives in the s_part region: qs + knew + vnew + red + sc
   const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + static_cast<size_t>(MG_G) * (chunk_max + 1)) * 4;
