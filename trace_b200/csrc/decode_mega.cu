@@ -114,7 +114,8 @@ __device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
     const int32_t* table = p.block_table + static_cast<size_t>(p.st.slot_ids[c->b]) * p.max_pages;
     const int p0 = c->start / p.page_size;
     const int np = (c->end > c->start) ? (c->end - 1) / p.page_size - p0 + 1 : 0;
-    for (int i = threadIdx.x; i < np && i < 64; i += GV_CONS) c->pages[i] = table[p0 + i];
+    // unused entries point at page 0 (always mapped): predicated-off lanes still form addresses from pages[0]
+    for (int i = threadIdx.x; i < 64; i += GV_CONS) c->pages[i] = (i < np) ? table[p0 + i] : 0;
     if (threadIdx.x == 64) c->page_new = table[c->t / p.page_size];
     if (threadIdx.x < MG_HD / 2) {
       c->cs[threadIdx.x] = p.cos_tab[static_cast<size_t>(c->t) * (MG_HD / 2) + threadIdx.x];
