@@ -61,4 +61,10 @@ if os.environ.get("TRACE_B200_MEGA_TIMING"):
         print(f"cta{c}: " + " ".join(f"{n}={float(d[:, i].mean()):.2f}" for i, n in enumerate(names)) + f" sync0={float(nxt.mean()):.2f} layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()):.2f} us")
         for nm, st0, k in (("qkv", 0, 10), ("o", 4, 12), ("gateup", 6, 14), ("down", 8, 16)):
             print(f"   {nm}: stage_x={float((x[:, k] - x[:, st0]).mean()):.2f} consume={float((x[:, k + 1] - x[:, k]).mean()):.2f} epilogue={float((x[:, st0 + 1] - x[:, k + 1]).mean()):.2f}")
+if os.environ.get("TRACE_B200_MEGA_TIMING"):
+    for c in range(2):
+        x = tl[c, 1:-1]
+        pts = [x[:, 2], x[:, 20], x[:, 21], x[:, 22], x[:, 23], x[:, 24], x[:, 3]]
+        nm = ["q+rope", "K/V+scores", "softmax", "PV+reduce", "partials+atomic", "merge(last)"]
+        print(f"   cta{c} attn: " + " ".join(f"{n}={float((pts[i + 1] - pts[i]).mean()):.2f}" for i, n in enumerate(nm)))
 print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f} box_copy_GBs={BOX_GBS:.0f} floor_ms_at_box_bw={14.0e9 / BOX_GBS / 1e6:.3f}")

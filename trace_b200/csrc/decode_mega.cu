@@ -88,6 +88,14 @@ struct MegaParams {
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
 };
 
+__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
+  if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 32 + k] = t;
+  }
+}
+
 // Per-step attention control block of this CTA's (fixed) work item: everything that would otherwise be a chain of
 // dependent global loads inside every layer's attention phase (pos -> slot -> block table -> row address; RoPE row).
 struct AttnCtl {
@@ -128,7 +136,7 @@ __device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
 // ------------------------------------------------------------------------------------------------
 // attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch) {
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl) {
   const int b = ctl.b, kv = ctl.kv, split = ctl.split;
   float* qs = scratch;                           // [4][128]
   float* knew = qs + MG_G * MG_HD;               // [128]
@@ -175,6 +183,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     }
   }
   cons_sync();
+  stamp(p, dl, 20);
   const int start = ctl.start;
   const int end = ctl.end;
   const int nloc = max(end - start, 0);
@@ -230,6 +239,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     ntot = nloc + 1;
   }
   cons_sync();
+  stamp(p, dl, 21);
   float mx = -INFINITY, l = 0.f;
   if (warp < MG_G) {
     float* s = sc + warp * cpitch;
@@ -243,6 +253,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     l = warp_sum(l);
   }
   cons_sync();
+  stamp(p, dl, 22);
   // phase B: lane <-> 4 dims, warps stride over keys, 8 keys per pass with the loads up front
   float o[MG_G][4];
 #pragma unroll
@@ -293,6 +304,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   for (int h = 0; h < MG_G; ++h)
     *reinterpret_cast<float4*>(red + (warp * MG_G + h) * MG_HD + lane * 4) = make_float4(o[h][0], o[h][1], o[h][2], o[h][3]);
   cons_sync();
+  stamp(p, dl, 23);
   const size_t pbase = (static_cast<size_t>(b) * kvh + kv) * nsplit + split;
   if (tid < 128) {
     float4 a = *reinterpret_cast<const float4*>(red + tid * 4);
@@ -314,6 +326,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     s_last = (old == nsplit - 1);
   }
   cons_sync();
+  stamp(p, dl, 24);
   if (s_last) {     // the last split of this (row, kv head) combines the partials -> attn [B, heads*128] fp16
     if (tid < 128) {
       const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
@@ -428,14 +441,6 @@ __device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLay
     const size_t off = ((static_cast<size_t>(c.pages[key / p.page_size - pg0]) * p.kvh + c.kv) * p.page_size + key % p.page_size) * MG_HD + (i & 1) * 64;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(L.k_pool + off));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(L.v_pool + off));
-  }
-}
-
-__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
-  if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 20 + k] = t;
   }
 }
 
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
     {
-      if (ctl->valid) attn_item(p, L, *ctl, m.s_part);
+      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l);
     }
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete

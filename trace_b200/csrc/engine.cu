@@ -225,7 +225,7 @@ int allocate_all(trace_b200_ctx* ctx) {
       dalloc(ctx, &ctx->st.slot_ids, kMaxB, true))
     return 1;
   if (dalloc(ctx, &ctx->d_gbar, 4, true)) return 1;
-  if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 20, true)) return 1;
+  if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 32, true)) return 1;
   {
     const char* env = getenv("TRACE_B200_DECODE_PEROP");
     ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
@@ -729,7 +729,7 @@ int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx) { return ctx ? ctx->weight_
 int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity) {
   TB_CHECK(ctx != nullptr && out_host != nullptr, "null argument");
   TB_CHECK(ctx->d_dbg != nullptr, "timeline not enabled (set TRACE_B200_MEGA_TIMING=1 before creating the context)");
-  const int n = 2 * ctx->c.layers * 20;
+  const int n = 2 * ctx->c.layers * 32;
   TB_CHECK(capacity >= n, "timeline buffer too small");
   TB_CUDA(cudaMemcpy(out_host, ctx->d_dbg, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost));
   return 0;

@@ -219,10 +219,10 @@ class Engine:
         return ms.value, st.value
 
     def debug_timeline(self):
-        n = 2 * self.dims.layers * 20
+        n = 2 * self.dims.layers * 32
         buf = (ctypes.c_uint64 * n)()
         _check(self.lib.trace_b200_debug_timeline(self._h, buf, n))
-        return torch.tensor(list(buf), dtype=torch.int64).view(2, self.dims.layers, 20)
+        return torch.tensor(list(buf), dtype=torch.int64).view(2, self.dims.layers, 32)
 
     @property
     def weight_bytes(self) -> int:
