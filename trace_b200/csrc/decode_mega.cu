@@ -136,32 +136,7 @@ __device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
 // ------------------------------------------------------------------------------------------------
 // attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
 // ------------------------------------------------------------------------------------------------
-// K (this lane's half row of key warp*16 + lane/2) and V (4 dims of keys warp + 8u) of the first 128 keys of the chunk:
-// requested BEFORE the grid barrier that publishes q/k/v -- cached rows do not depend on this step, and demand loads
-// issued after the barrier queue behind ~20 MB of in-flight weight prefetch (measured 5.5 us), so they travel during
-// the barrier wait instead.
-struct AttnPre { uint4 k[8]; uint2 v[16]; };
-__device__ __forceinline__ void attn_preload(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, AttnPre& pre) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nloc = max(ctl.end - ctl.start, 0);
-  const int pg0 = ctl.start / p.page_size;
-  {
-    const int j = warp * 16 + (lane >> 1);
-    const int key = ctl.start + (j < nloc ? j : 0);
-    const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / p.page_size - pg0]) * p.kvh + ctl.kv) * p.page_size + key % p.page_size) * MG_HD + (lane & 1) * 64;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) pre.k[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
-  }
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int j = warp + u * GV_WARPS;
-    const int key = ctl.start + (j < nloc ? j : 0);
-    pre.v[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[key / p.page_size - pg0]) * p.kvh + ctl.kv) * p.page_size + key % p.page_size) * MG_HD + lane * 4);
-  }
-}
-
-__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl,
-                                          const AttnPre& pre) {
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl) {
   const int b = ctl.b, kv = ctl.kv, split = ctl.split;
   float* qs = scratch;                           // [4][128]
   float* knew = qs + MG_G * MG_HD;               // [128]
@@ -212,6 +187,15 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   const int start = ctl.start;
   const int end = ctl.end;
   const int nloc = max(end - start, 0);
+  // the first 16 V rows of this warp are requested now, together with the K rows (one memory round trip for both)
+  uint2 vpre[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int j = warp + u * GV_WARPS;
+    const int key = start + (j < nloc ? j : 0);
+    const int page = ctl.pages[key / page_size - pg0];
+    vpre[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
+  }
   // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
   for (int base = warp * 16; base < nloc; base += GV_WARPS * 16) {
     const int j = base + (lane >> 1);
@@ -221,13 +205,8 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     const int page = ctl.pages[key / page_size - pg0];
     const __half* kr = L.k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
     uint4 kreg[8];
-    if (base < 128) {                 // first pass: rows preloaded before the barrier
 #pragma unroll
-      for (int c = 0; c < 8; ++c) kreg[c] = pre.k[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
-    }
+    for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
     float acc[MG_G] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -283,7 +262,7 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   for (int u = 0; u < 16; ++u) {
     const int j = warp + u * GV_WARPS;
     if (j < nloc) {
-      const float2 v0 = unpack_half2(pre.v[u].x), v1 = unpack_half2(pre.v[u].y);
+      const float2 v0 = unpack_half2(vpre[u].x), v1 = unpack_half2(vpre[u].y);
 #pragma unroll
       for (int h = 0; h < MG_G; ++h) {
         const float pr = sc[h * cpitch + j];
@@ -580,12 +559,10 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     stamp(p, l, 0);
     gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
     stamp(p, l, 1);
-    AttnPre pre;
-    if (ctl->valid) attn_preload(p, L, *ctl, pre);
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
     {
-      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, pre);
+      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l);
     }
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
