@@ -136,7 +136,8 @@ __device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
 // ------------------------------------------------------------------------------------------------
 // attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl) {
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl,
+                                          volatile int* gate) {
   const int b = ctl.b, kv = ctl.kv, split = ctl.split;
   float* qs = scratch;                           // [4][128]
   float* knew = qs + MG_G * MG_HD;               // [128]
@@ -196,6 +197,17 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     const int page = ctl.pages[key / page_size - pg0];
     vpre[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
   }
+  uint4 kfirst[8];
+  {
+    const int j = warp * 16 + (lane >> 1);
+    const int key = start + (j < nloc ? j : 0);
+    const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + (lane & 1) * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kfirst[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+  }
+  // the latency-critical K/V requests are in the memory system: only now may the producer warp start flooding the HBM
+  // queues with the O-projection weights (demand loads issued behind ~20 MB of queued weight traffic took 5.5 us)
+  if (tid == 0) *gate = dl + 1;
   // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
   for (int base = warp * 16; base < nloc; base += GV_WARPS * 16) {
     const int j = base + (lane >> 1);
@@ -205,8 +217,13 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     const int page = ctl.pages[key / page_size - pg0];
     const __half* kr = L.k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
     uint4 kreg[8];
+    if (base < GV_WARPS * 16) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+      for (int c = 0; c < 8; ++c) kreg[c] = kfirst[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+    }
     float acc[MG_G] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -479,6 +496,8 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     m.empty = reinterpret_cast<uint64_t*>(smem + off);
     m.ws_stride = GV_TILE * (1024 + WS_PAD);   // fixed stage stride: phases with a smaller KS must not alias other stages
   }
+  __shared__ volatile int s_gate;     // layer index + 1 whose attention loads have been issued (consumers -> producer)
+  if (threadIdx.x == 0) s_gate = 0;
   gv_init_barriers(m, p.stages);
   const int ncta = gridDim.x;
   // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
@@ -530,6 +549,9 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
       }
       cta_rows(p.qkvw, r0, r1);
       gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
+      if ((threadIdx.x & 31) == 0)
+        while (s_gate < l + 1) { }
+      __syncwarp();
       cta_rows(p.H, r0, r1);
       gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
       cta_rows(2 * p.ffn, r0, r1);
@@ -562,7 +584,8 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
     {
-      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l);
+      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, &s_gate);
+      else if (threadIdx.x == 0) s_gate = l + 1;
     }
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
