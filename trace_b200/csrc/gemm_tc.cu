@@ -34,7 +34,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;       // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 8 * 2048;   // per-epilogue-warp transpose buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 struct EpiParams {
@@ -74,6 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_buf = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,8 +171,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = tm * BM, n0 = tn * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
@@ -183,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= N) continue;
+        if (col0 >= N) continue;                  // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -202,40 +202,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
         }
+        // Transpose through a per-warp 2 KB staging buffer so that every global store instruction writes whole 64-byte
+        // row segments (8 rows x 64 B) instead of 32 scattered 16-byte pieces of 32 different rows; the fp16 rounding
+        // of the linear output happens here, the residual is added to the rounded value (the reference's two roundings).
+        uint8_t* wbuf = epi_buf + (warp - 4) * 2048;
         if (ep.swiglu) {
-          // (gate, up) column pairs -> 16 outputs at column col0/2
-          __half* op = ep.out + static_cast<size_t>(row) * ep.ldo + (col0 >> 1);
+          // (gate, up) column pairs -> 16 outputs (32 B per row) at column col0/2
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
-            if (col0 + j8 * 16 < N) {
-              uint4 o;
-              o.x = pack_half2(silu(v[j8 * 16 + 0]) * v[j8 * 16 + 1], silu(v[j8 * 16 + 2]) * v[j8 * 16 + 3]);
-              o.y = pack_half2(silu(v[j8 * 16 + 4]) * v[j8 * 16 + 5], silu(v[j8 * 16 + 6]) * v[j8 * 16 + 7]);
-              o.z = pack_half2(silu(v[j8 * 16 + 8]) * v[j8 * 16 + 9], silu(v[j8 * 16 + 10]) * v[j8 * 16 + 11]);
-              o.w = pack_half2(silu(v[j8 * 16 + 12]) * v[j8 * 16 + 13], silu(v[j8 * 16 + 14]) * v[j8 * 16 + 15]);
-              *reinterpret_cast<uint4*>(op + j8 * 8) = o;
-            }
+            uint4 o;
+            o.x = pack_half2(silu(v[j8 * 16 + 0]) * v[j8 * 16 + 1], silu(v[j8 * 16 + 2]) * v[j8 * 16 + 3]);
+            o.y = pack_half2(silu(v[j8 * 16 + 4]) * v[j8 * 16 + 5], silu(v[j8 * 16 + 6]) * v[j8 * 16 + 7]);
+            o.z = pack_half2(silu(v[j8 * 16 + 8]) * v[j8 * 16 + 9], silu(v[j8 * 16 + 10]) * v[j8 * 16 + 11]);
+            o.w = pack_half2(silu(v[j8 * 16 + 12]) * v[j8 * 16 + 13], silu(v[j8 * 16 + 14]) * v[j8 * 16 + 15]);
+            *reinterpret_cast<uint4*>(wbuf + lane * 32 + j8 * 16) = o;
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int rr = i * 16 + (lane >> 1), j = lane & 1;
+            const uint4 o = *reinterpret_cast<const uint4*>(wbuf + rr * 32 + j * 16);
+            const int grow = m0 + q * 32 + rr;
+            if (grow < M && col0 + j * 16 < N)
+              *reinterpret_cast<uint4*>(ep.out + static_cast<size_t>(grow) * ep.ldo + (col0 >> 1) + j * 8) = o;
+          }
+          __syncwarp();
         } else {
-          __half* op = ep.out + static_cast<size_t>(row) * ep.ldo + col0;
-          const __half* rp = ep.residual ? ep.residual + static_cast<size_t>(row) * ep.ldr + col0 : nullptr;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            if (col0 + j8 * 8 < N) {
-              if (rp != nullptr) {
-                uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
-                float2 f0 = unpack_half2(b.x), f1 = unpack_half2(b.y), f2 = unpack_half2(b.z), f3 = unpack_half2(b.w);
-                v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
-                v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+            uint4 o;
+            o.x = pack_half2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+            o.y = pack_half2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+            o.z = pack_half2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+            o.w = pack_half2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(wbuf + lane * 64 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = o;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2), j = lane & 3;
+            uint4 o = *reinterpret_cast<const uint4*>(wbuf + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
+            const int grow = m0 + q * 32 + rr, gcol = col0 + j * 8;
+            if (grow < M && gcol < N) {
+              if (ep.residual != nullptr) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + gcol);
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) oh[k] = __hadd2(oh[k], rh[k]);
               }
-              uint4 o;
-              o.x = pack_half2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-              o.y = pack_half2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-              o.z = pack_half2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-              o.w = pack_half2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + j8 * 8) = o;
+              *reinterpret_cast<uint4*>(ep.out + static_cast<size_t>(grow) * ep.ldo + gcol) = o;
             }
           }
+          __syncwarp();
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
