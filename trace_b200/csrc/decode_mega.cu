@@ -349,27 +349,27 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
       const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
       const int h = tid >> 5;
       // all partial statistics first (independent loads -> one L2 round trip), then all partial outputs
-      float2 ml[32];
+      float2 ml[20];
 #pragma unroll
-      for (int s = 0; s < 32; ++s)
+      for (int s = 0; s < 20; ++s)
         ml[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float2*>(p.part_ml + (gb + s) * (MG_G * 2) + h * 2)) : make_float2(-INFINITY, 0.f);
       float M = -INFINITY;
 #pragma unroll
-      for (int s = 0; s < 32; ++s) M = fmaxf(M, ml[s].x);
+      for (int s = 0; s < 20; ++s) M = fmaxf(M, ml[s].x);
       float Lsum = 0.f;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        if (half * 16 < nsplit) {
-          float4 po[16];
+        if (half * 10 < nsplit) {
+          float4 po[10];
 #pragma unroll
-          for (int s = 0; s < 16; ++s)
-            po[s] = (half * 16 + s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + half * 16 + s) * (MG_G * MG_HD) + tid * 4))
+          for (int s = 0; s < 10; ++s)
+            po[s] = (half * 10 + s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (gb + half * 10 + s) * (MG_G * MG_HD) + tid * 4))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int s = 0; s < 16; ++s) {
-            const float2 m2 = ml[half * 16 + s];
-            if (half * 16 + s < nsplit && m2.y != 0.f) {
+          for (int s = 0; s < 10; ++s) {
+            const float2 m2 = ml[half * 10 + s];
+            if (half * 10 + s < nsplit && m2.y != 0.f) {
               const float w = __expf(m2.x - M);
               Lsum += w * m2.y;
               acc.x += w * po[s].x; acc.y += w * po[s].y; acc.z += w * po[s].z; acc.w += w * po[s].w;
@@ -695,7 +695,7 @@ static int pick_ks2(int KP) {
 int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int max_ctx, int kvh, int num_sms, int* nsplit_out,
                      int* chunk_max_out, int* kp_ks /*[10]*/, int* max_tiles_out, int* stages_out, int* xs_cap_out, size_t* smem_out) {
   TB_CHECK(B >= 1 && B <= GV_MAXB, "decode batch must be in [1, 8]");
-  const size_t xcap = 64 * 1024;
+  const size_t xcap = 72 * 1024;   // B=8 x (4096 + pad) halves must fit (fused RMSNorm stages the whole hidden row)
   const int Ks[5] = {H, qd, H, ffn, H};
   int kpmax = 0;
   for (int i = 0; i < 5; ++i) {
@@ -715,7 +715,7 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   }
   int nsplit = num_sms / (B * kvh);
   if (nsplit < 1) nsplit = 1;
-  if (nsplit > 32) nsplit = 32;
+  if (nsplit > 20) nsplit = 20;      // the merge keeps all split statistics in registers
   TB_CHECK(B * kvh * nsplit <= num_sms, "one attention work item per CTA");
   TB_CHECK((max_ctx + nsplit - 1) / nsplit <= 62 * 64, "attention chunk exceeds the per-CTA page table (64 pages)");
   const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
