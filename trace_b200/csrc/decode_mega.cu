@@ -84,7 +84,8 @@ struct MegaParams {
   unsigned *gbar, *gexit;
   int kp_qkv, ks_qkv, kp_o, ks_o, kp_gu, ks_gu, kp_dn, ks_dn, kp_hd, ks_hd;
   unsigned long long* dbg;            // optional timeline [2 CTAs][layers][10] of %globaltimer stamps
-  int pf_ahead;                       // L2 prefetch distance of the weight stream, in stages
+  int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
+  int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
 };
 
@@ -461,6 +462,23 @@ __device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLay
   }
 }
 
+// While the consumer warps are about to idle in a grid barrier (or in the latency-bound attention phase) the HBM pipe
+// drains: the producer's shared-memory ring (4 x 33 KB) only covers ~3 us of streaming.  The consumers therefore ask L2
+// for the part of their NEXT weight rows that lies beyond the ring (this CTA's rows of a row-major matrix are one
+// contiguous byte range) with plain prefetch.global.L2 hints -- LSU work on otherwise idle threads, nothing added to the
+// TMA queue -- so that the ring refills from L2 instead of HBM when the phase starts.
+__device__ __forceinline__ void prefetch_next_rows(const __half* W, int K, int N, int skip_rows, int max_kb) {
+  if (max_kb <= 0) return;
+  int r0, r1;
+  cta_rows(N, r0, r1);
+  const long long avail = static_cast<long long>(r1 - r0 - skip_rows) * K * 2;
+  if (avail <= 0) return;
+  const long long bytes = avail < static_cast<long long>(max_kb) * 1024 ? avail : static_cast<long long>(max_kb) * 1024;
+  const char* base = reinterpret_cast<const char*>(W + static_cast<size_t>(r0 + skip_rows) * K);
+  for (long long off = static_cast<long long>(threadIdx.x) * 128; off < bytes; off += static_cast<long long>(GV_CONS) * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
 template <int PRO, int EPI>
 __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
@@ -577,10 +595,13 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     const MegaLayer L = p.L[l];
     GammaRegs gm = load_gamma(L.ln1, p.H);                                    // weights: issued before the barrier
     attn_prefetch(p, L, *ctl);
+    if (l > 0) prefetch_next_rows(L.qkv_w, p.H, p.qkvw, GV_TILE, p.pf_gap_kb);
     if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
     stamp(p, l, 0);
     gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
     stamp(p, l, 1);
+    prefetch_next_rows(L.o_w, p.qd, p.H, GV_TILE, p.pf_attn_kb);               // the attention gap is long: O + start of gate/up
+    prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, 0, p.pf_attn_kb);
     grid_sync(p.gbar, target);                                                // q, k, v complete
     stamp(p, l, 2);
     {
@@ -593,10 +614,12 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, s, ph, l, 12);
     stamp(p, l, 5);
     gm = load_gamma(L.ln2, p.H);
+    prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, GV_TILE + (p.pf_attn_kb * 1024) / (p.H * 2), p.pf_gap_kb);
     grid_sync(p.gbar, target);
     stamp(p, l, 6);
     gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, s, ph, l, 14);
     stamp(p, l, 7);
+    prefetch_next_rows(L.down_w, p.ffn, p.H, 4, p.pf_gap_kb);
     grid_sync(p.gbar, target);
     stamp(p, l, 8);
     gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, s, ph, l, 16);
@@ -756,6 +779,15 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
       pf = (e != nullptr && atoi(e) >= 0 && atoi(e) <= 64) ? atoi(e) : 0;
     }
     p.pf_ahead = pf;
+    static int gap_kb = -1, attn_kb = -1;
+    if (gap_kb < 0) {
+      const char* e1 = getenv("TRACE_B200_PF_GAP_KB");
+      const char* e2 = getenv("TRACE_B200_PF_ATTN_KB");
+      gap_kb = (e1 != nullptr && atoi(e1) >= 0 && atoi(e1) <= 4096) ? atoi(e1) : 128;
+      attn_kb = (e2 != nullptr && atoi(e2) >= 0 && atoi(e2) <= 4096) ? atoi(e2) : 384;
+    }
+    p.pf_gap_kb = gap_kb;
+    p.pf_attn_kb = attn_kb;
   }
   p.dbg = a.dbg;
   int kpks[10];
