@@ -139,12 +139,17 @@ __device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl,
                                           volatile int* gate) {
+  // Warp-autonomous split-KV attention: every warp owns 16 keys per pass, keeps an online-softmax state (m, l, o) for
+  // the 4 query heads of this kv head in registers and only meets the other warps once, for the CTA-level merge.
+  //   scores : 2 lanes per key (64 dims each, 8 x 16-byte loads), pair-reduced with one shuffle
+  //   PV     : lane <-> 4 dims, the 16 probabilities of the pass are broadcast with shuffles
+  // All K and V rows of a pass are requested up front (one memory round trip per pass).
   const int b = ctl.b, kv = ctl.kv, split = ctl.split;
-  float* qs = scratch;                           // [4][128]
-  float* knew = qs + MG_G * MG_HD;               // [128]
-  float* vnew = knew + MG_HD;                    // [128]
-  float* red = vnew + MG_HD;                     // [8 warps][4][128]
-  float* sc = red + GV_WARPS * MG_G * MG_HD;     // [4][chunk_max + 1]
+  float* qs = scratch;                                   // [4][128]  (pre-scaled, RoPE'd q)
+  float* knew = qs + MG_G * MG_HD;                       // [128]
+  float* vnew = knew + MG_HD;                            // [128]
+  float* red_o = vnew + MG_HD;                           // [8 warps][4][128]
+  float* red_ml = red_o + GV_WARPS * MG_G * MG_HD;       // [8 warps][4][2]
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int heads = p.heads, kvh = p.kvh, nsplit = p.nsplit, page_size = p.page_size;
@@ -152,7 +157,6 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   const int pg0 = ctl.start / page_size;
   const __half* row = p.qkv + static_cast<size_t>(b) * p.qkvw;
   const float scale = rsqrtf(static_cast<float>(MG_HD));
-  const int cpitch = p.chunk_max + 1;
   const float* cs = ctl.cs;
   const float* sn = ctl.sn;
   for (int i = tid; i < MG_G * (MG_HD / 2); i += GV_CONS) {
@@ -184,47 +188,38 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
       vnew[d + 1] = f.y;
     }
   }
-  cons_sync();
-  stamp(p, dl, 20);
   const int start = ctl.start;
-  const int end = ctl.end;
-  const int nloc = max(end - start, 0);
-  // the first 16 V rows of this warp are requested now, together with the K rows (one memory round trip for both)
-  uint2 vpre[16];
+  const int nloc = max(ctl.end - start, 0);
+  float m_w[MG_G], l_w[MG_G], o_w[MG_G][4];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int j = warp + u * GV_WARPS;
-    const int key = start + (j < nloc ? j : 0);
-    const int page = ctl.pages[key / page_size - pg0];
-    vpre[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
-  }
-  uint4 kfirst[8];
-  {
-    const int j = warp * 16 + (lane >> 1);
-    const int key = start + (j < nloc ? j : 0);
-    const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + (lane & 1) * 64;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) kfirst[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
-  }
-  // the latency-critical K/V requests are in the memory system: only now may the producer warp start flooding the HBM
-  // queues with the O-projection weights (demand loads issued behind ~20 MB of queued weight traffic took 5.5 us)
-  if (tid == 0) *gate = dl + 1;
-  // phase A: 2 lanes per key, 16 keys per warp per pass, 8 x 16-byte loads per lane issued up front
-  for (int base = warp * 16; base < nloc; base += GV_WARPS * 16) {
-    const int j = base + (lane >> 1);
-    const int hf = lane & 1;
-    const bool valid = j < nloc;
-    const int key = start + (valid ? j : 0);
-    const int page = ctl.pages[key / page_size - pg0];
-    const __half* kr = L.k_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
+  for (int h = 0; h < MG_G; ++h) { m_w[h] = -INFINITY; l_w[h] = 0.f; o_w[h][0] = o_w[h][1] = o_w[h][2] = o_w[h][3] = 0.f; }
+  const int hf = lane & 1;
+  bool first = true;
+  for (int base = 0; base < nloc || first; base += GV_WARPS * 16) {
+    // ---- request this pass's rows: K half row of key (warp*16 + lane/2), V 4-dim slices of the warp's 16 keys ----
+    const int jk = base + warp * 16 + (lane >> 1);
+    const bool kvalid = jk < nloc;
     uint4 kreg[8];
-    if (base < GV_WARPS * 16) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kreg[c] = kfirst[c];
-    } else {
+    uint2 vreg[16];
+    {
+      const int key = start + (kvalid ? jk : 0);
+      const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
 #pragma unroll
       for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int j = base + warp * 16 + u;
+        const int keyv = start + (j < nloc ? j : 0);
+        vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
+      }
     }
+    if (first) {
+      if (tid == 0) *gate = dl + 1;          // latency-critical requests are out: the producer may start the O weights
+      cons_sync();                            // qs / knew / vnew visible
+      stamp(p, dl, 20);
+      first = false;
+    }
+    // ---- scores of the pair's key ----
     float acc[MG_G] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -239,104 +234,84 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
       }
     }
 #pragma unroll
-    for (int h = 0; h < MG_G; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
-    if (valid && hf == 0) {
+    for (int h = 0; h < MG_G; ++h) {
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+      if (!kvalid) acc[h] = -INFINITY;
+      // online softmax update with the warp's 16 keys
+      float mx = acc[h];
 #pragma unroll
-      for (int h = 0; h < MG_G; ++h) sc[h * cpitch + j] = acc[h];
+      for (int o = 2; o <= 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float mn = fmaxf(m_w[h], mx);
+      const float pr = (mn == -INFINITY) ? 0.f : __expf(acc[h] - mn);       // both lanes of a pair hold the same value
+      const float corr = (mn == -INFINITY) ? 1.f : __expf(m_w[h] - mn);
+      float ps = hf == 0 ? pr : 0.f;
+#pragma unroll
+      for (int o = 1; o <= 16; o <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      l_w[h] = l_w[h] * corr + ps;
+      m_w[h] = mn;
+      o_w[h][0] *= corr; o_w[h][1] *= corr; o_w[h][2] *= corr; o_w[h][3] *= corr;
+      acc[h] = pr;
+    }
+    // ---- O += P V : lane <-> 4 dims, probabilities broadcast from the lane pair that owns the key ----
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float2 v0 = unpack_half2(vreg[u].x), v1 = unpack_half2(vreg[u].y);
+#pragma unroll
+      for (int h = 0; h < MG_G; ++h) {
+        const float pr = __shfl_sync(0xffffffffu, acc[h], 2 * u);
+        o_w[h][0] += pr * v0.x; o_w[h][1] += pr * v0.y; o_w[h][2] += pr * v1.x; o_w[h][3] += pr * v1.y;
+      }
     }
   }
-  int ntot = nloc;
-  if (split == 0) {
-    if (warp < MG_G) {
+  if (split == 0 && warp == 0) {   // the token being decoded attends to itself: key/value from shared memory, not the cache
+#pragma unroll
+    for (int h = 0; h < MG_G; ++h) {
       float d = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d += qs[warp * MG_HD + lane * 4 + i] * knew[lane * 4 + i];
+      for (int i = 0; i < 4; ++i) d += qs[h * MG_HD + lane * 4 + i] * knew[lane * 4 + i];
       d = warp_sum(d);
-      if (lane == 0) sc[warp * cpitch + nloc] = d;
+      const float mn = fmaxf(m_w[h], d);
+      const float pr = __expf(d - mn), corr = __expf(m_w[h] - mn);
+      l_w[h] = l_w[h] * corr + pr;
+      m_w[h] = mn;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o_w[h][i] = o_w[h][i] * corr + pr * vnew[lane * 4 + i];
     }
-    ntot = nloc + 1;
   }
-  cons_sync();
   stamp(p, dl, 21);
-  float mx = -INFINITY, l = 0.f;
-  if (warp < MG_G) {
-    float* s = sc + warp * cpitch;
-    for (int j = lane; j < ntot; j += 32) mx = fmaxf(mx, s[j]);
-    mx = warp_max(mx);
-    for (int j = lane; j < ntot; j += 32) {
-      const float pr = __expf(s[j] - mx);
-      s[j] = pr;
-      l += pr;
-    }
-    l = warp_sum(l);
+  // ---- CTA-level merge of the 8 warps ----
+#pragma unroll
+  for (int h = 0; h < MG_G; ++h) {
+    *reinterpret_cast<float4*>(red_o + (warp * MG_G + h) * MG_HD + lane * 4) = make_float4(o_w[h][0], o_w[h][1], o_w[h][2], o_w[h][3]);
+    if (lane == 0) { red_ml[(warp * MG_G + h) * 2] = m_w[h]; red_ml[(warp * MG_G + h) * 2 + 1] = l_w[h]; }
   }
   cons_sync();
   stamp(p, dl, 22);
-  // phase B: lane <-> 4 dims, warps stride over keys, 8 keys per pass with the loads up front
-  float o[MG_G][4];
-#pragma unroll
-  for (int h = 0; h < MG_G; ++h) o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int j = warp + u * GV_WARPS;
-    if (j < nloc) {
-      const float2 v0 = unpack_half2(vpre[u].x), v1 = unpack_half2(vpre[u].y);
-#pragma unroll
-      for (int h = 0; h < MG_G; ++h) {
-        const float pr = sc[h * cpitch + j];
-        o[h][0] += pr * v0.x; o[h][1] += pr * v0.y; o[h][2] += pr * v1.x; o[h][3] += pr * v1.y;
-      }
-    }
-  }
-  for (int j0 = warp + 16 * GV_WARPS; j0 < nloc; j0 += GV_WARPS * 8) {
-    uint2 vreg[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u * GV_WARPS;
-      const int key = start + (j < nloc ? j : 0);
-      const int page = ctl.pages[key / page_size - pg0];
-      vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(page) * kvh + kv) * page_size + key % page_size) * MG_HD + lane * 4);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u * GV_WARPS;
-      if (j < nloc) {
-        const float2 v0 = unpack_half2(vreg[u].x), v1 = unpack_half2(vreg[u].y);
-#pragma unroll
-        for (int h = 0; h < MG_G; ++h) {
-          const float pr = sc[h * cpitch + j];
-          o[h][0] += pr * v0.x; o[h][1] += pr * v0.y; o[h][2] += pr * v1.x; o[h][3] += pr * v1.y;
-        }
-      }
-    }
-  }
-  if (split == 0 && warp == 0) {
-#pragma unroll
-    for (int h = 0; h < MG_G; ++h) {
-      const float pr = sc[h * cpitch + nloc];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[h][i] += pr * vnew[lane * 4 + i];
-    }
-  }
-#pragma unroll
-  for (int h = 0; h < MG_G; ++h)
-    *reinterpret_cast<float4*>(red + (warp * MG_G + h) * MG_HD + lane * 4) = make_float4(o[h][0], o[h][1], o[h][2], o[h][3]);
-  cons_sync();
-  stamp(p, dl, 23);
   const size_t pbase = (static_cast<size_t>(b) * kvh + kv) * nsplit + split;
   if (tid < 128) {
-    float4 a = *reinterpret_cast<const float4*>(red + tid * 4);
+    const int h = tid >> 5;
+    float M = -INFINITY;
 #pragma unroll
-    for (int w = 1; w < GV_WARPS; ++w) {
-      const float4 x4 = *reinterpret_cast<const float4*>(red + w * MG_G * MG_HD + tid * 4);
-      a.x += x4.x; a.y += x4.y; a.z += x4.z; a.w += x4.w;
+    for (int w = 0; w < GV_WARPS; ++w) M = fmaxf(M, red_ml[(w * MG_G + h) * 2]);
+    float Ls = 0.f;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < GV_WARPS; ++w) {
+      const float mw = red_ml[(w * MG_G + h) * 2], lw = red_ml[(w * MG_G + h) * 2 + 1];
+      if (lw != 0.f) {
+        const float wt = __expf(mw - M);
+        Ls += wt * lw;
+        const float4 x4 = *reinterpret_cast<const float4*>(red_o + (w * MG_G + h) * MG_HD + (tid & 31) * 4);
+        a.x += wt * x4.x; a.y += wt * x4.y; a.z += wt * x4.z; a.w += wt * x4.w;
+      }
     }
     __stcg(reinterpret_cast<float4*>(p.part_o + pbase * (MG_G * MG_HD) + tid * 4), a);
+    if ((tid & 31) == 0) {
+      __stcg(p.part_ml + pbase * (MG_G * 2) + h * 2, M);
+      __stcg(p.part_ml + pbase * (MG_G * 2) + h * 2 + 1, Ls);
+    }
   }
-  if (warp < MG_G && lane == 0) {
-    __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2, mx);
-    __stcg(p.part_ml + pbase * (MG_G * 2) + warp * 2 + 1, l);
-  }
+  stamp(p, dl, 23);
   cons_sync();
   if (tid == 0) {   // acq_rel: releases this CTA's partials (cumulative over the bar.sync) and acquires the others'
     int old;
@@ -349,7 +324,6 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
     if (tid < 128) {
       const size_t gb = (static_cast<size_t>(b) * kvh + kv) * nsplit;
       const int h = tid >> 5;
-      // all partial statistics first (independent loads -> one L2 round trip), then all partial outputs
       float2 ml[20];
 #pragma unroll
       for (int s = 0; s < 20; ++s)
@@ -743,7 +717,7 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   TB_CHECK((max_ctx + nsplit - 1) / nsplit <= 62 * 64, "attention chunk exceeds the per-CTA page table (64 pages)");
   const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
   // attention scratch lives in the s_part region: qs + knew + vnew + red + sc
-  const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + static_cast<size_t>(MG_G) * (chunk_max + 1)) * 4;
+  const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + GV_WARPS * MG_G * 2) * 4;
   size_t part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
   while (part_bytes < attn_scratch) { ++max_tiles; part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4; }
   const int xs_cap = kpmax + XS_PAD;
@@ -783,8 +757,8 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
     if (gap_kb < 0) {
       const char* e1 = getenv("TRACE_B200_PF_GAP_KB");
       const char* e2 = getenv("TRACE_B200_PF_ATTN_KB");
-      gap_kb = (e1 != nullptr && atoi(e1) >= 0 && atoi(e1) <= 4096) ? atoi(e1) : 128;
-      attn_kb = (e2 != nullptr && atoi(e2) >= 0 && atoi(e2) <= 4096) ? atoi(e2) : 384;
+      gap_kb = (e1 != nullptr && atoi(e1) >= 0 && atoi(e1) <= 4096) ? atoi(e1) : 0;
+      attn_kb = (e2 != nullptr && atoi(e2) >= 0 && atoi(e2) <= 4096) ? atoi(e2) : 0;
     }
     p.pf_gap_kb = gap_kb;
     p.pf_attn_kb = attn_kb;
