@@ -36,7 +36,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // ---- activation staging into shared memory: xs[b][k], b < B, k in [k0, k0+KP) --------------------------------
 // executed by the 256 consumer threads only.  Activations are read with ld.global.cg (other CTAs rewrite them
 // between the phases of the fused decode step).
-__device__ __noinline__ void stage_x_plain(__half* xs, const __half* x, int ldx, int B, int k0, int KP) {
+__device__ __forceinline__ void stage_x_plain(__half* xs, const __half* x, int ldx, int B, int k0, int KP) {
   const int pitch = KP + XS_PAD;
   for (int b = 0; b < B; ++b)
     for (int i = threadIdx.x; i < KP / 8; i += GV_CONS)
@@ -59,7 +59,7 @@ __device__ __forceinline__ GammaRegs load_gamma(const __half* gamma, int K) {
 // HF MistralRMSNorm (fp32 mean of squares over the full row, x*rstd rounded to fp16, then weight * that in fp16)
 // fused into the staging: ONE read of x (kept in registers across the reduction), one barrier pair.  K <= 4096.
 template <int NB>
-__device__ __noinline__ void stage_x_rmsnorm_nb(__half* xs, const __half* x, int ldx, int B, int K, const GammaRegs& gm, float eps,
+__device__ __forceinline__ void stage_x_rmsnorm_nb(__half* xs, const __half* x, int ldx, int B, int K, const GammaRegs& gm, float eps,
                                                    float* s_red) {
   const int tid = threadIdx.x;
   const int pitch = K + XS_PAD;
@@ -191,7 +191,7 @@ struct GvItems {
 // the previous kernel / phase, so this warp never waits for activations and runs up to `stages` stages ahead in
 // shared memory plus `pf_ahead` further stages ahead in L2 (cp.async.bulk.prefetch.L2): while the consumers sit in a
 // barrier the HBM pipe keeps draining the next rows into L2, and the ring refills from L2 when they resume.
-__device__ __noinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
+__device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
                                               int vhi, const GvSmem& m, int stages, int& s, uint32_t& ph, int pf_ahead = 0) {
   const int lane = threadIdx.x & 31;
   const int pitch = KS + WS_PAD;
@@ -225,7 +225,7 @@ __device__ __noinline__ void gemv_producer(const __half* __restrict__ W, int K, 
 }
 
 // ---- consumer warps: MMA over the staged tiles; partial sums per (tile, warp) in shared memory ---------------
-__device__ __noinline__ void gemv_consume_phase(int k0, int KP, int KS, int r0, int r1, int vlo, int vhi, const GvSmem& m,
+__device__ __forceinline__ void gemv_consume_phase(int k0, int KP, int KS, int r0, int r1, int vlo, int vhi, const GvSmem& m,
                                                    int B, int stages, int& s, uint32_t& ph) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;

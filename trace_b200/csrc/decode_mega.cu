@@ -41,7 +41,8 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
 }
 
 // epilogues of the GEMV phases (256 consumer threads, after the partials are complete)
-__device__ __noinline__ void gemv_epilogue(int EPI, const GvSmem& m, int r0, int r1, int B, __half* out, int ldo) {
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo) {
   const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
   for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
     const float v = gemv_out(m.s_part, idx);
@@ -103,7 +104,7 @@ struct AttnCtl {
   int pages[64];            // page id of key range page i (i = key/page_size - start/page_size)
   float cs[MG_HD / 2], sn[MG_HD / 2];
 };
-__device__ __noinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
+__device__ __forceinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
   const int items = p.B * p.kvh * p.nsplit;
   const int it = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -136,7 +137,7 @@ __device__ __noinline__ void attn_ctl_init(const MegaParams& p, AttnCtl* c) {
 // ------------------------------------------------------------------------------------------------
 // attention work item (b, kv, split) on the 8 consumer warps; scratch lives in the s_part/xs region
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl,
+__device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& L, const AttnCtl& ctl, float* scratch, int dl,
                                           volatile int* gate) {
   // Warp-autonomous split-KV attention: every warp owns 16 keys per pass, keeps an online-softmax state (m, l, o) for
   // the 4 query heads of this kv head in registers and only meets the other warps once, for the CTA-level merge.
@@ -364,7 +365,7 @@ __device__ __noinline__ void attn_item(const MegaParams& p, const MegaLayer& L, 
 // ------------------------------------------------------------------------------------------------
 // finalize (CTA 0, 256 consumer threads)
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void finalize_step(const MegaParams& p, int ncand) {
+__device__ __forceinline__ void finalize_step(const MegaParams& p, int ncand) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   __shared__ int s_tok[GV_MAXB];
@@ -423,7 +424,7 @@ __device__ __noinline__ void finalize_step(const MegaParams& p, int ncand) {
 
 // Pull this CTA's K/V slice of layer L towards L2 while the other CTAs are still finishing the QKV phase: the cached
 // rows do not depend on this step's q/k/v, so their HBM latency is taken off the attention critical path.
-__device__ __noinline__ void attn_prefetch(const MegaParams& p, const MegaLayer& L, const AttnCtl& c) {
+__device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLayer& L, const AttnCtl& c) {
   if (!c.valid) return;
   const int pg0 = c.start / p.page_size;
   // one 128-byte line per thread per pass: 2 lines per key row (256 B), K then V
@@ -440,7 +441,7 @@ __device__ __noinline__ void attn_prefetch(const MegaParams& p, const MegaLayer&
 // for the part of their NEXT weight rows that lies beyond the ring (this CTA's rows of a row-major matrix are one
 // contiguous byte range) with plain prefetch.global.L2 hints -- LSU work on otherwise idle threads, nothing added to the
 // TMA queue -- so that the ring refills from L2 instead of HBM when the phase starts.
-__device__ __noinline__ void prefetch_next_rows(const __half* W, int K, int N, int skip_rows, int max_kb) {
+__device__ __forceinline__ void prefetch_next_rows(const __half* W, int K, int N, int skip_rows, int max_kb) {
   if (max_kb <= 0) return;
   int r0, r1;
   cta_rows(N, r0, r1);
@@ -453,7 +454,8 @@ __device__ __noinline__ void prefetch_next_rows(const __half* W, int K, int N, i
 }
 
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
-__device__ __noinline__ void gemv_phase_cons(int PRO, int EPI, const MegaParams& p, const GvSmem& m, const __half* xin, int ldx, __half* out, int ldo,
+template <int PRO, int EPI>
+__device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
                                                 int N, int K, int KP, int KS, const GammaRegs& gm, int& s, uint32_t& ph,
                                                 int dl = 0, int dk = -1) {
   int r0, r1;
@@ -469,7 +471,7 @@ __device__ __noinline__ void gemv_phase_cons(int PRO, int EPI, const MegaParams&
   }
   cons_sync();
   if (dk >= 0) stamp(p, dl, dk + 1);
-  gemv_epilogue(EPI, m, r0, r1, p.B, out, ldo);
+  gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
 }
 
 __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     if (l > 0) prefetch_next_rows(L.qkv_w, p.H, p.qkvw, GV_TILE, p.pf_gap_kb);
     if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
     stamp(p, l, 0);
-    gemv_phase_cons(1, 0, p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
+    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
     stamp(p, l, 1);
     prefetch_next_rows(L.o_w, p.qd, p.H, GV_TILE, p.pf_attn_kb);               // the attention gap is long: O + start of gate/up
     prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, 0, p.pf_attn_kb);
@@ -583,18 +585,18 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     stamp(p, l, 3);
     grid_sync(p.gbar, target);                                                // attention output complete
     stamp(p, l, 4);
-    gemv_phase_cons(0, 1, p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, s, ph, l, 12);
+    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, s, ph, l, 12);
     stamp(p, l, 5);
     gm = load_gamma(L.ln2, p.H);
     prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, GV_TILE + (p.pf_attn_kb * 1024) / (p.H * 2), p.pf_gap_kb);
     grid_sync(p.gbar, target);
     stamp(p, l, 6);
-    gemv_phase_cons(1, 2, p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, s, ph, l, 14);
+    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, s, ph, l, 14);
     stamp(p, l, 7);
     prefetch_next_rows(L.down_w, p.ffn, p.H, 4, p.pf_gap_kb);
     grid_sync(p.gbar, target);
     stamp(p, l, 8);
-    gemv_phase_cons(0, 1, p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, s, ph, l, 16);
+    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, s, ph, l, 16);
     stamp(p, l, 9);
   }
   const GammaRegs gmf = load_gamma(p.final_norm, p.H);
