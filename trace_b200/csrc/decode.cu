@@ -68,7 +68,7 @@ gemv_kernel(const __half* __restrict__ W, const __half* __restrict__ x, int ldx,
 int pick_kp(int K, int B) {
   // largest multiple of 256 that divides K with the staged activations (B rows) <= 64 KB
   for (int kp = 16384; kp >= 256; kp -= 256)
-    if (K % kp == 0 && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= 64 * 1024) return kp;
+    if (K % kp == 0 && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= 72 * 1024) return kp;
   return 0;
 }
 int pick_ks(int KP) {
