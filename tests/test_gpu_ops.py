@@ -57,6 +57,21 @@ def test_gemm_epilogues():
     _close(E.op_gemm(a, w, swiglu=True), want, 2e-3, 4e-3, "swiglu")
 
 
+def test_gemm_wide_tiles_all_epilogues():
+    """Shapes that take the 256x256 two-CTA (cta_group::2) path: ragged M, every epilogue."""
+    from trace_b200 import engine as E
+    M, N, K = 5003, 2048, 320
+    a, w, bias, res = _rand((M, K), 1.0, 31), _rand((N, K), 0.05, 32), _rand((N,), 0.5, 33), _rand((M, N), 1.0, 34)
+    base = a.float() @ w.float().t()
+    _close(E.op_gemm(a, w), base, 2e-3, 4e-3, "wide plain")
+    _close(E.op_gemm(a, w, bias=bias, act=1), (base + bias.float()) * torch.sigmoid(1.702 * (base + bias.float())), 2e-3, 4e-3, "wide gelu")
+    _close(E.op_gemm(a, w, bias=bias, residual=res), base + bias.float() + res.float(), 2e-3, 6e-3, "wide residual")
+    _close(E.op_gemm(a, w, swiglu=True), torch.nn.functional.silu(base[:, 0::2]) * base[:, 1::2], 2e-3, 4e-3, "wide swiglu")
+    M, N, K = 18464, 1024, 1024
+    a, w = _rand((M, K), 1.0, 35), _rand((N, K), 0.03, 36)
+    _close(E.op_gemm(a, w), a.float() @ w.float().t(), 2e-3, 6e-3, "vit-shaped")
+
+
 def test_norms():
     from trace_b200 import engine as E
     for D in (128, 192, 1024, 4096):
