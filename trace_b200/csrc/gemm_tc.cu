@@ -47,8 +47,10 @@ struct EpiParams {
   int swiglu;              // 1: columns are (gate,up) pairs -> N/2 outputs silu(gate)*up
 };
 
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(a x) with ex2.approx + rcp.approx (relative error ~1e-7, far below the fp16 rounding of the output); the
+// IEEE division costs ~8 extra issue slots per element and the K=1024 ViT GEMMs are epilogue-issue bound
+__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // bias / activation / SwiGLU + fp16 rounding + per-warp transpose + coalesced (residual-adding) stores of one 32-column chunk
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], uint8_t* wbuf, int lane, int row_base, int col0, int M, int N) {
