@@ -54,6 +54,16 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 
 // bias / activation / SwiGLU + fp16 rounding + per-warp transpose + coalesced (residual-adding) stores of one 32-column chunk
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], uint8_t* wbuf, int lane, int row_base, int col0, int M, int N) {
+        // residual rows in the (post-transpose) store layout: requested first so their latency hides behind the math below
+        uint4 rv[4];
+        if (ep.residual != nullptr && !ep.swiglu) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grow = row_base + i * 8 + (lane >> 2), gcol = col0 + (lane & 3) * 8;
+            rv[i] = (grow < M && gcol < N) ? *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + gcol)
+                                           : make_uint4(0, 0, 0, 0);
+          }
+        }
         if (ep.bias != nullptr) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
@@ -111,9 +121,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
             const int grow = row_base + rr, gcol = col0 + j * 8;
             if (grow < M && gcol < N) {
               if (ep.residual != nullptr) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + gcol);
                 __half2* oh = reinterpret_cast<__half2*>(&o);
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) oh[k] = __hadd2(oh[k], rh[k]);
               }
