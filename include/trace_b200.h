@@ -113,6 +113,9 @@ int trace_b200_op_rmsnorm(const void* x, const void* w, float eps, void* out, in
 int trace_b200_op_attention(const void* q, const void* k, const void* v, void* o, int seqlen, int q_stride,
                             int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride,
                             int heads, int group, int batch, int head_dim, int causal, float scale, void* stream);
+/* tcgen05 / TMEM attention over a fused [batch*seqlen, (heads+2*kv_heads)*head_dim] activation */
+int trace_b200_op_attention_tc(const void* qkv, int width, void* o, int seqlen, int heads, int kv_heads, int head_dim, int causal,
+                               int batch, float scale, void* stream);
 int trace_b200_op_gemv(const void* W, const void* x, void* out, int B, int N, int K, int pro, const void* gamma,
                        float eps, int epi, void* stream);
 

@@ -87,10 +87,12 @@ def test_norms():
 @pytest.mark.parametrize("B,S,heads,kvh,hd,causal", [(3, 577, 2, 2, 64, False), (2, 17, 2, 2, 64, False),
                                                      (2, 200, 32, 8, 128, True), (1, 67, 32, 8, 128, True),
                                                      (1, 1000, 8, 2, 128, True)])
-def test_attention(B, S, heads, kvh, hd, causal):
+@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
+def test_attention(B, S, heads, kvh, hd, causal, impl):
     from trace_b200 import engine as E
     qkv = _rand((B, S, (heads + 2 * kvh) * hd), 1.0, 11)
-    out = E.op_attention(qkv, heads, kvh, hd, causal)
+    out = (E.op_attention if impl == "mma_sync" else E.op_attention_tc)(qkv, heads, kvh, hd, causal)
+    torch.cuda.synchronize()
     q = qkv[..., : heads * hd].float().view(B, S, heads, hd).transpose(1, 2)
     k = qkv[..., heads * hd: (heads + kvh) * hd].float().view(B, S, kvh, hd).transpose(1, 2)
     v = qkv[..., (heads + kvh) * hd:].float().view(B, S, kvh, hd).transpose(1, 2)

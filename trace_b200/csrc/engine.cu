@@ -91,6 +91,7 @@ struct trace_b200_ctx {
   unsigned* d_gbar = nullptr;
   unsigned long long* d_dbg = nullptr;
   bool fused_decode = true;
+  bool attn_tc = false;           // tcgen05 attention (attention_tc.cu) instead of the mma.sync kernel
 };
 
 namespace {
@@ -229,6 +230,8 @@ int allocate_all(trace_b200_ctx* ctx) {
   {
     const char* env = getenv("TRACE_B200_DECODE_PEROP");
     ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
+    const char* env2 = getenv("TRACE_B200_ATTN_TC");
+    ctx->attn_tc = (env2 != nullptr) ? atoi(env2) == 1 : false;
   }
   // ---- KV pool ----
   const size_t page_elems = static_cast<size_t>(c.kv_heads) * kPage * c.head_dim;
@@ -368,9 +371,14 @@ int vit_chunk(trace_b200_ctx* ctx, const __half* pixels, int F, __half* res_out,
   for (const VitLayer& l : ctx->vit) {
     RUN(layernorm_f16(ctx->v_h, D, l.ln1_w, l.ln1_b, c.vit_ln_eps, ctx->v_y, D, M, D, s));
     RUN(gemm_f16(ctx->v_y, D, l.qkv_w, D, ctx->v_qkv, 3 * D, M, 3 * D, D, l.qkv_b, nullptr, 0, 0, 0, sms, s));
-    RUN(attention_fwd(ctx->v_qkv, ctx->v_qkv + D, ctx->v_qkv + 2 * D, ctx->v_attn, NT, 3 * D, 3 * D, D,
-                      static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * D,
-                      c.vit_heads, 1, F, hdv, 0, 1.0f / sqrtf(static_cast<float>(hdv)), s));
+    if (ctx->attn_tc) {
+      RUN(attention_tc_fwd(ctx->v_qkv, 3 * D, ctx->v_attn, NT, D, static_cast<int64_t>(NT) * D, 0, D, 2 * D, c.vit_heads, 1, F, hdv, 0,
+                           1.0f / sqrtf(static_cast<float>(hdv)), s));
+    } else {
+      RUN(attention_fwd(ctx->v_qkv, ctx->v_qkv + D, ctx->v_qkv + 2 * D, ctx->v_attn, NT, 3 * D, 3 * D, D,
+                        static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * D,
+                        c.vit_heads, 1, F, hdv, 0, 1.0f / sqrtf(static_cast<float>(hdv)), s));
+    }
     RUN(gemm_f16(ctx->v_attn, D, l.out_w, D, ctx->v_h, D, M, D, D, l.out_b, ctx->v_h, D, 0, 0, sms, s));
     RUN(layernorm_f16(ctx->v_h, D, l.ln2_w, l.ln2_b, c.vit_ln_eps, ctx->v_y, D, M, D, s));
     RUN(gemm_f16(ctx->v_y, D, l.fc1_w, D, ctx->v_mlp, c.vit_mlp, M, c.vit_mlp, D, l.fc1_b, nullptr, 0, 1, 0, sms, s));
@@ -395,9 +403,14 @@ int decoder_layers_prefill(trace_b200_ctx* ctx, int B, int S, const int32_t* slo
     RUN(gemm_f16(ctx->p_y, H, l.qkv_w, H, ctx->p_qkv, ctx->qkvw, M, ctx->qkvw, H, nullptr, nullptr, 0, 0, 0, sms, s));
     RUN(rope_kv_prefill(ctx->p_qkv, B, S, c.heads, c.kv_heads, c.head_dim, ctx->rope_cos, ctx->rope_sin, ctx->k_pool[i],
                         ctx->v_pool[i], ctx->d_block_table, slot_ids_dev, ctx->max_pages_seq, kPage, s));
-    RUN(attention_fwd(ctx->p_qkv, ctx->p_qkv + qd, ctx->p_qkv + qd + kvd, ctx->p_attn, S, ctx->qkvw, ctx->qkvw, qd,
-                      static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * qd,
-                      c.heads, c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
+    if (ctx->attn_tc) {
+      RUN(attention_tc_fwd(ctx->p_qkv, ctx->qkvw, ctx->p_attn, S, qd, static_cast<int64_t>(S) * qd, 0, qd, qd + kvd, c.heads,
+                           c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
+    } else {
+      RUN(attention_fwd(ctx->p_qkv, ctx->p_qkv + qd, ctx->p_qkv + qd + kvd, ctx->p_attn, S, ctx->qkvw, ctx->qkvw, qd,
+                        static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * qd,
+                        c.heads, c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
+    }
     RUN(gemm_f16(ctx->p_attn, qd, l.o_w, qd, ctx->p_h, H, M, H, qd, nullptr, ctx->p_h, H, 0, 0, sms, s));
     RUN(rmsnorm_f16(ctx->p_h, H, l.ln2, c.rms_eps, ctx->p_y, H, M, H, s));
     RUN(gemm_f16(ctx->p_y, H, l.gateup_w, H, ctx->p_act, c.ffn, M, 2 * c.ffn, H, nullptr, nullptr, 0, 0, 1, sms, s));
@@ -767,6 +780,12 @@ int trace_b200_op_attention(const void* q, const void* k, const void* v, void* o
   return attention_fwd(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
                        static_cast<__half*>(o), seqlen, q_stride, kv_stride, o_stride, q_bstride, kv_bstride, o_bstride, heads, group,
                        batch, head_dim, causal, scale, static_cast<cudaStream_t>(stream));
+}
+int trace_b200_op_attention_tc(const void* qkv, int width, void* o, int seqlen, int heads, int kv_heads, int head_dim, int causal, int batch,
+                               float scale, void* stream) {
+  const int qd = heads * head_dim, kvd = kv_heads * head_dim;
+  return attention_tc_fwd(static_cast<const __half*>(qkv), width, static_cast<__half*>(o), seqlen, qd, static_cast<int64_t>(seqlen) * qd, 0, qd,
+                          qd + kvd, heads, heads / kv_heads, batch, head_dim, causal, scale, static_cast<cudaStream_t>(stream));
 }
 int trace_b200_op_gemv(const void* W, const void* x, void* out, int B, int N, int K, int pro, const void* gamma, float eps, int epi,
                        void* stream) {

@@ -33,6 +33,11 @@ int attention_fwd(const __half* Q, const __half* K, const __half* V, __half* O, 
                   int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride, int heads,
                   int group, int batch, int head_dim, int causal, float scale, cudaStream_t stream);
 
+// ---- attention_tc.cu : the same contraction on tcgen05 (TMA-fed, S / PV accumulators in TMEM) ------------------
+// qkv: fused activation [batch*seqlen, width]; Q/K/V heads at column offsets q_col0/k_col0/v_col0 (head h -> + h*HD).
+int attention_tc_fwd(const __half* qkv, int width, __half* O, int seqlen, int o_stride, int64_t o_bstride, int q_col0, int k_col0,
+                     int v_col0, int heads, int group, int batch, int head_dim, int causal, float scale, cudaStream_t stream);
+
 // ---- projector.cu : fused SpatialSlotPool up to the slot-weighted sums --------------------------------------
 // feats: rows of width D with pitch ld; frame f owns rows [f*frame_rows + row_off, +n).  res [F*8, D] fp16.
 int slot_pool_fused(const __half* feats, int ld, int frame_rows, int row_off, int n, int D, int F,

@@ -22,7 +22,7 @@ EXPORTS = [
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
     "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
-    "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_gemv",
+    "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_op_rmsnorm.argtypes = [vp, vp, f32, vp, i32, i32, vp]
     lib.trace_b200_op_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32,
                                             f32, vp]
+    lib.trace_b200_op_attention_tc.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.trace_b200_op_gemv.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, f32, i32, vp]
     _lib = lib
     return lib
@@ -265,6 +266,17 @@ def op_attention(qkv: torch.Tensor, heads: int, kv_heads: int, head_dim: int, ca
     base = qkv.data_ptr()
     _check(lib.trace_b200_op_attention(base, base + qd * 2, base + (qd + kvd) * 2, out.data_ptr(), S, W, W, qd, S * W, S * W,
                                        S * qd, heads, heads // kv_heads, B, head_dim, int(causal), head_dim ** -0.5, _stream()))
+    return out
+
+
+def op_attention_tc(qkv: torch.Tensor, heads: int, kv_heads: int, head_dim: int, causal: bool) -> torch.Tensor:
+    """tcgen05/TMEM attention; same contract as op_attention."""
+    lib = load_library()
+    qkv = _f16c(qkv)
+    B, S, W = qkv.shape
+    out = torch.empty((B, S, heads * head_dim), dtype=torch.float16, device=qkv.device)
+    _check(lib.trace_b200_op_attention_tc(qkv.data_ptr(), W, out.data_ptr(), S, heads, kv_heads, head_dim, int(causal), B,
+                                          head_dim ** -0.5, _stream()))
     return out
 
 
