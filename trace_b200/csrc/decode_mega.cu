@@ -28,16 +28,184 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
+// ------------------------------------------------------------------------------------------------
+// TMEM weight reservoir.
+//
+// The shared-memory ring (4-5 stages x 33 KB) covers only ~3 us of this SM's share of the HBM stream; every grid
+// barrier (+ epilogue + activation staging) is a 5-7 us hole in which the ring is full, the producer stalls and
+// the HBM pipe drains.  Tensor memory (256 KB per SM) is otherwise unused by this kernel, so the consumer warps use
+// it as 8 more stages: while they wait in a grid barrier they keep taking full stages out of the ring, park their
+// OWN mma fragments of the stage in TMEM (tcgen05.st: thread-private lane x 32 columns per stage -> no layout
+// contract with anybody) and hand the stage back to the producer, which keeps streaming.  After the barrier the
+// parked stages are read back with tcgen05.ld and fed to the same mma.sync sequence as a ring stage.
+//
+// Determinism: a row tile is always accumulated in one register accumulator in k order, whether its stages come
+// from TMEM, from the ring or from both; only the ORDER IN WHICH TILES ARE VISITED depends on how many stages
+// happened to be parked, so results are bit-identical run to run.
+// ------------------------------------------------------------------------------------------------
+constexpr int TM_SLOTS = 8;            // parked stages per thread: 8 x 32 columns; warps w and w+4 share a lane quadrant
+constexpr int TM_COLS = 512;
+
+struct Stream {                        // consumer-side view of the weight stream (uniform over the 256 consumer threads)
+  int s;                               // ring stage of the next item
+  uint32_t ph;
+  int tm_head, tm_count;               // FIFO of parked stages (always older than anything in the ring)
+  int seq, seq_left;                   // phase sequence number of the ring-front item, items of it not yet taken from the ring
+  int seq_end;                         // layers*4 + 1
+  uint32_t tm_base;                    // this thread's TMEM address: lane quadrant of the warp, column half of the warp
+  int enabled;
+};
+struct StreamTab {                     // per-CTA item geometry of the 5 phase types (qkv, o, gate/up, down, head)
+  int cnt[5], ks[5];
+  volatile int code[2];
+};
+__device__ __forceinline__ int seq_type(int seq, int seq_end) { return seq == seq_end - 1 ? 4 : (seq & 3); }
+__device__ __forceinline__ void stream_skip_empty(Stream& st, const StreamTab& tab) {
+  while (st.seq_left == 0 && st.seq < st.seq_end) {
+    ++st.seq;
+    st.seq_left = st.seq < st.seq_end ? tab.cnt[seq_type(st.seq, st.seq_end)] : 0;
+  }
+}
+__device__ __forceinline__ void stream_ring_advance(Stream& st, int stages) {
+  if (++st.s == stages) { st.s = 0; st.ph ^= 1; }
+}
+
+// move the ring-front stage into TMEM (all 256 consumer threads; the caller has seen full[s] complete)
+__device__ __forceinline__ void relay_one(Stream& st, const StreamTab& tab, const GvSmem& m, int stages) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int KS = tab.ks[seq_type(st.seq, st.seq_end)];
+  const int ksw = KS / GV_WARPS, nch = ksw / 32, wpitch = KS + WS_PAD;
+  mbar_wait(&m.full[st.s], st.ph);
+  const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
+  const __half* wb = wa + 8 * wpitch;
+  uint32_t r[32];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (ch < nch) {
+      a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+      b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+    }
+    r[ch * 8 + 0] = a.x; r[ch * 8 + 1] = a.y; r[ch * 8 + 2] = a.z; r[ch * 8 + 3] = a.w;
+    r[ch * 8 + 4] = b.x; r[ch * 8 + 5] = b.y; r[ch * 8 + 6] = b.z; r[ch * 8 + 7] = b.w;
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&m.empty[st.s]);          // the stage is in registers: the producer may refill it
+  tmem_st_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + st.tm_count) & (TM_SLOTS - 1)) * 32u, r);
+  tmem_st_wait();
+  stream_ring_advance(st, stages);
+  ++st.tm_count;
+  --st.seq_left;
+  stream_skip_empty(st, tab);
+}
+
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, const GvSmem& m, int stages) {
   cons_sync();
+  target += gridDim.x;
   if (threadIdx.x == 0) {
-    target += gridDim.x;
     // release-reduction: orders every write this CTA made before the bar.sync above (cumulativity) without a separate
     // membar.gl + atomic round trip; the acquire loads below pair with it
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    while (ld_acquire_u32(bar) < target) { }
   }
-  cons_sync();
+  if (!st.enabled) {
+    if (threadIdx.x == 0)
+      while (ld_acquire_u32(bar) < target) { }
+    cons_sync();
+    return;
+  }
+  // wait for the other CTAs; meanwhile park arriving stages in TMEM so that the producer never stops streaming
+  for (int it = 0;; ++it) {
+    if (threadIdx.x == 0) {
+      int code = 0;
+      if (ld_acquire_u32(bar) >= target) code = 2;
+      else if (st.tm_count < TM_SLOTS && st.seq_left > 0 && mbar_test(&m.full[st.s], st.ph)) code = 1;
+      tab.code[it & 1] = code;
+    }
+    cons_sync();
+    const int code = tab.code[it & 1];
+    if (code == 2) break;
+    if (code == 1) relay_one(st, tab, m, stages);
+  }
+}
+
+// One k-phase of one matrix on the consumer side: the first min(tm_count, items) items of the phase are parked in
+// TMEM, the rest comes through the ring.  Ring tiles and TMEM tiles are visited alternately so that ring stages are
+// handed back to the producer from the first microsecond of the phase.
+__device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, int k0, int KP, int KS, int r0, int r1, int vlo,
+                                              int vhi, const GvSmem& m, int B, int stages) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
+  const int ksw = KS / GV_WARPS;                  // columns of a stage owned by this warp (multiple of 32)
+  const int nch = ksw / 32;
+  const int wpitch = KS + WS_PAD;
+  const int nks = KP / KS;
+  const bool xok = g < B;
+  int tlo = 0, thi = 0;                           // tiles with a needed row: [tlo, thi)
+  if (vlo < vhi) { tlo = (vlo - r0) / GV_TILE; thi = (vhi - 1 - r0) / GV_TILE + 1; }
+  if (k0 == 0) {
+    for (int tile = 0; tile < ntile; ++tile) {
+      if (tile >= tlo && tile < thi) continue;
+      float* p = m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * 8);
+      p[g * 8 + 2 * t] = 0.f; p[g * 8 + 2 * t + 1] = 0.f; p[(g + 8) * 8 + 2 * t] = 0.f; p[(g + 8) * 8 + 2 * t + 1] = 0.f;
+    }
+  }
+  const int nvt = thi - tlo;
+  const int n_items = nvt * nks;
+  const int n_tm = min(st.tm_count, n_items);
+  const int ts = n_tm / nks;                      // tiles [0, ts) come from TMEM only; tile ts starts in TMEM (maybe 0 items)
+  const __half* xbase = m.xs + g * (KP + XS_PAD) + warp * ksw + t * 8;
+  int ta = 0, tr = ts;
+  while (tr < nvt || ta < ts) {
+    int vt;
+    if (tr < nvt && (ta >= ts || ((tr - ts) <= ta))) vt = tr++;
+    else vt = ta++;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < nks; ++j) {
+      const int i = vt * nks + j;
+      const __half* xp = xbase + j * KS;
+      if (i < n_tm) {
+        uint32_t rr[32];
+        tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + i) & (TM_SLOTS - 1)) * 32u, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < nch) {
+            const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
+            mma_16816(c, rr[ch * 8 + 0], rr[ch * 8 + 4], rr[ch * 8 + 1], rr[ch * 8 + 5], xv.x, xv.y);
+            mma_16816(c, rr[ch * 8 + 2], rr[ch * 8 + 6], rr[ch * 8 + 3], rr[ch * 8 + 7], xv.z, xv.w);
+          }
+        }
+      } else {
+        mbar_wait(&m.full[st.s], st.ph);
+        const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
+        const __half* wb = wa + 8 * wpitch;
+#pragma unroll 4
+        for (int ch = 0; ch < nch; ++ch) {
+          const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+          const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+          const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
+          mma_16816(c, a.x, b.x, a.y, b.y, xv.x, xv.y);
+          mma_16816(c, a.z, b.z, a.w, b.w, xv.z, xv.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&m.empty[st.s]);
+        stream_ring_advance(st, stages);
+      }
+    }
+    float* p = m.s_part + (static_cast<size_t>(tlo + vt) * GV_WARPS + warp) * (GV_TILE * 8);
+    if (k0 > 0) {
+      p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
+      p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
+    } else {
+      p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
+      p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+    }
+  }
+  st.tm_head = (st.tm_head + n_tm) & (TM_SLOTS - 1);
+  st.tm_count -= n_tm;
+  st.seq_left -= n_items - n_tm;                  // ring items of a phase are only taken once its parked items are used up
+  stream_skip_empty(st, tab);
 }
 
 // epilogues of the GEMV phases (256 consumer threads, after the partials are complete)
@@ -87,6 +255,8 @@ struct MegaParams {
   int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
   int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
   int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+  int tm_relay;                       // park ring stages in TMEM while waiting in grid barriers (0 = off)
+  int gate_mode;                      // producer waits for the attention K/V requests before: 1 the O weights, 2 the gate/up weights, 0 never
 };
 
 __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
@@ -456,7 +626,7 @@ __device__ __forceinline__ void prefetch_next_rows(const __half* W, int K, int N
 // one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
 template <int PRO, int EPI>
 __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
-                                                int N, int K, int KP, int KS, const GammaRegs& gm, int& s, uint32_t& ph,
+                                                int N, int K, int KP, int KS, const GammaRegs& gm, Stream& st, const StreamTab& tab,
                                                 int dl = 0, int dk = -1) {
   int r0, r1;
   cta_rows(N, r0, r1);
@@ -466,8 +636,8 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
     else stage_x_plain(m.xs, xin, ldx, p.B, k0, KP);
     cons_sync();
     if (dk >= 0 && k0 == 0) stamp(p, dl, dk);
-    // the staged row pitch is KP + XS_PAD: gemv_consume_phase derives it from KP
-    gemv_consume_phase(k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages, s, ph);
+    // the staged row pitch is KP + XS_PAD: consume_phase derives it from KP
+    consume_phase(st, tab, k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages);
   }
   cons_sync();
   if (dk >= 0) stamp(p, dl, dk + 1);
@@ -489,8 +659,13 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     m.ws_stride = GV_TILE * (1024 + WS_PAD);   // fixed stage stride: phases with a smaller KS must not alias other stages
   }
   __shared__ volatile int s_gate;     // layer index + 1 whose attention loads have been issued (consumers -> producer)
+  __shared__ uint32_t s_tmem;
+  __shared__ StreamTab s_tab;
   if (threadIdx.x == 0) s_gate = 0;
+  if (p.tm_relay && threadIdx.x < 32) tmem_alloc(&s_tmem, TM_COLS);   // whole TMEM: one CTA per SM by shared-memory footprint
+  tc_fence_before();
   gv_init_barriers(m, p.stages);
+  tc_fence_after();
   const int ncta = gridDim.x;
   // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
   // late producer warp must not see the new values or it would stream rows that nobody consumes)
@@ -541,11 +716,18 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
       }
       cta_rows(p.qkvw, r0, r1);
       gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
-      if ((threadIdx.x & 31) == 0)
-        while (s_gate < l + 1) { }
-      __syncwarp();
+      if (p.gate_mode == 1) {
+        if ((threadIdx.x & 31) == 0)
+          while (s_gate < l + 1) { }
+        __syncwarp();
+      }
       cta_rows(p.H, r0, r1);
       gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
+      if (p.gate_mode == 2) {
+        if ((threadIdx.x & 31) == 0)
+          while (s_gate < l + 1) { }
+        __syncwarp();
+      }
       cta_rows(2 * p.ffn, r0, r1);
       gemv_producer(L.gateup_w, p.H, p.kp_gu, p.ks_gu, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
       cta_rows(p.H, r0, r1);
@@ -563,44 +745,66 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   AttnCtl* ctl = &s_ctl;
   attn_ctl_init(p, ctl);
   unsigned target = 0;
-  int s = 0;
-  uint32_t ph = 0;
+  // ---- weight-stream bookkeeping: items per phase type for THIS CTA (must mirror the producer's enumeration) ----
+  int hd_r0, hd_r1;
+  cta_rows(p.head_rows, hd_r0, hd_r1);
+  const int hd_vlo = max(ulo, hd_r0), hd_vhi = min(uhi, hd_r1);
+  if (threadIdx.x == 0) {
+    int r0, r1;
+    cta_rows(p.qkvw, r0, r1);
+    s_tab.cnt[0] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.H / p.ks_qkv);
+    cta_rows(p.H, r0, r1);
+    s_tab.cnt[1] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.qd / p.ks_o);
+    s_tab.cnt[3] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.ffn / p.ks_dn);
+    cta_rows(2 * p.ffn, r0, r1);
+    s_tab.cnt[2] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.H / p.ks_gu);
+    s_tab.cnt[4] = hd_vlo < hd_vhi ? ((hd_vhi - 1 - hd_r0) / GV_TILE - (hd_vlo - hd_r0) / GV_TILE + 1) * (p.H / p.ks_hd) : 0;
+    s_tab.ks[0] = p.ks_qkv; s_tab.ks[1] = p.ks_o; s_tab.ks[2] = p.ks_gu; s_tab.ks[3] = p.ks_dn; s_tab.ks[4] = p.ks_hd;
+  }
+  cons_sync();
+  Stream st;
+  st.s = 0; st.ph = 0; st.tm_head = 0; st.tm_count = 0;
+  st.seq_end = p.layers * 4 + 1;
+  st.seq = 0; st.seq_left = s_tab.cnt[0];
+  stream_skip_empty(st, s_tab);
+  st.enabled = p.tm_relay;
+  st.tm_base = p.tm_relay ? s_tmem + (static_cast<uint32_t>(32 * ((threadIdx.x >> 5) & 3)) << 16) + static_cast<uint32_t>((threadIdx.x >> 7) * (TM_SLOTS * 32)) : 0u;
   for (int l = 0; l < p.layers; ++l) {
     const MegaLayer L = p.L[l];
     GammaRegs gm = load_gamma(L.ln1, p.H);                                    // weights: issued before the barrier
     attn_prefetch(p, L, *ctl);
     if (l > 0) prefetch_next_rows(L.qkv_w, p.H, p.qkvw, GV_TILE, p.pf_gap_kb);
-    if (l > 0) grid_sync(p.gbar, target);                                     // residual stream complete
+    if (l > 0) grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                     // residual stream complete
     stamp(p, l, 0);
-    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, s, ph, l, 10);
+    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, st, s_tab, l, 10);
     stamp(p, l, 1);
     prefetch_next_rows(L.o_w, p.qd, p.H, GV_TILE, p.pf_attn_kb);               // the attention gap is long: O + start of gate/up
     prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, 0, p.pf_attn_kb);
-    grid_sync(p.gbar, target);                                                // q, k, v complete
+    grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                                // q, k, v complete
     stamp(p, l, 2);
     {
       if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, &s_gate);
       else if (threadIdx.x == 0) s_gate = l + 1;
     }
     stamp(p, l, 3);
-    grid_sync(p.gbar, target);                                                // attention output complete
+    grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                                // attention output complete
     stamp(p, l, 4);
-    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, s, ph, l, 12);
+    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, st, s_tab, l, 12);
     stamp(p, l, 5);
     gm = load_gamma(L.ln2, p.H);
     prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, GV_TILE + (p.pf_attn_kb * 1024) / (p.H * 2), p.pf_gap_kb);
-    grid_sync(p.gbar, target);
+    grid_sync(p.gbar, target, st, s_tab, m, p.stages);
     stamp(p, l, 6);
-    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, s, ph, l, 14);
+    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, st, s_tab, l, 14);
     stamp(p, l, 7);
     prefetch_next_rows(L.down_w, p.ffn, p.H, 4, p.pf_gap_kb);
-    grid_sync(p.gbar, target);
+    grid_sync(p.gbar, target, st, s_tab, m, p.stages);
     stamp(p, l, 8);
-    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, s, ph, l, 16);
+    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, st, s_tab, l, 16);
     stamp(p, l, 9);
   }
   const GammaRegs gmf = load_gamma(p.final_norm, p.H);
-  grid_sync(p.gbar, target);
+  grid_sync(p.gbar, target, st, s_tab, m, p.stages);
   // ---- heads: final RMSNorm + logits of the active ranges + argmax candidates ----
   {
     int r0, r1;
@@ -615,7 +819,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     if (vlo < vhi) {
       stage_x_rmsnorm(m.xs, p.x, p.H, p.B, p.H, gmf, p.eps, m.s_red);
       cons_sync();
-      gemv_consume_phase(0, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.B, p.stages, s, ph);
+      consume_phase(st, s_tab, 0, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.B, p.stages);
       cons_sync();
       int lo = 0, hi = 0;
 #pragma unroll
@@ -655,10 +859,14 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
       __stcg(p.cand_idx + threadIdx.x * ncta + blockIdx.x, i);
     }
   }
-  grid_sync(p.gbar, target);
+  grid_sync(p.gbar, target, st, s_tab, m, p.stages);
   if (blockIdx.x == 0) finalize_step(p, ncta);
   // exit protocol: the last CTA to leave resets the barrier counters for the next launch
   cons_sync();
+  if (p.tm_relay && threadIdx.x < 32) {
+    __syncwarp();
+    tmem_dealloc(s_tmem, TM_COLS);
+  }
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(p.gexit, 1u) == static_cast<unsigned>(ncta) - 1) {
@@ -762,6 +970,17 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
     }
     p.pf_gap_kb = gap_kb;
     p.pf_attn_kb = attn_kb;
+  }
+  {
+    static int relay = -1, gate = -1;
+    if (relay < 0) {
+      const char* e = getenv("TRACE_B200_TM_RELAY");
+      relay = (e != nullptr) ? (atoi(e) != 0) : 1;
+      const char* g = getenv("TRACE_B200_GATE_MODE");
+      gate = (g != nullptr && atoi(g) >= 0 && atoi(g) <= 2) ? atoi(g) : (relay ? 2 : 1);
+    }
+    p.tm_relay = relay;
+    p.gate_mode = gate;
   }
   p.dbg = a.dbg;
   int kpks[10];
