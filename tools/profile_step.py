@@ -67,4 +67,9 @@ if os.environ.get("TRACE_B200_MEGA_TIMING"):
         pts = [x[:, 2], x[:, 20], x[:, 21], x[:, 22], x[:, 23], x[:, 24], x[:, 3]]
         nm = ["q+rope", "K/V+scores", "softmax", "PV+reduce", "partials+atomic", "merge(last)"]
         print(f"   cta{c} attn: " + " ".join(f"{n}={float((pts[i + 1] - pts[i]).mean()):.2f}" for i, n in enumerate(nm)))
+if os.environ.get("TRACE_B200_MEGA_TIMING"):
+    raw = model.engine.debug_timeline()
+    for c in range(2):
+        print(f"   cta{c} stages parked in TMEM at phase start: " + " ".join(
+            f"{n}={float(raw[c, 1:-1, 25 + i].double().mean()):.2f}" for i, n in enumerate(["qkv", "o", "gateup", "down"])))
 print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f} box_copy_GBs={BOX_GBS:.0f} floor_ms_at_box_bw={14.0e9 / BOX_GBS / 1e6:.3f}")

@@ -58,7 +58,10 @@ struct Stream {                        // consumer-side view of the weight strea
 struct StreamTab {                     // per-CTA item geometry of the 5 phase types (qkv, o, gate/up, down, head)
   int cnt[5], ks[5];
   volatile int code[2];
+  volatile unsigned arrived;           // consumers -> poller warp: barrier target this CTA has arrived at (0xffffffff = quit)
+  volatile unsigned released;          // poller warp -> consumers: last barrier target seen complete
 };
+constexpr int MG_THREADS = GV_THREADS + 32;   // 8 consumer warps + producer warp + barrier poller warp
 __device__ __forceinline__ int seq_type(int seq, int seq_end) { return seq == seq_end - 1 ? 4 : (seq & 3); }
 __device__ __forceinline__ void stream_skip_empty(Stream& st, const StreamTab& tab) {
   while (st.seq_left == 0 && st.seq < st.seq_end) {
@@ -113,12 +116,18 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Strea
     cons_sync();
     return;
   }
-  // wait for the other CTAs; meanwhile park arriving stages in TMEM so that the producer never stops streaming
+  // wait for the other CTAs; meanwhile park arriving stages in TMEM so that the producer never stops streaming.
+  // The barrier word itself is watched by the poller warp (an L2 round trip under full HBM load is 1-2 us: a blocking
+  // poll between two parked stages would cap the relay at one stage per round trip); it reports through shared memory.
+  if (threadIdx.x == 0) tab.arrived = target;
+  int patience = st.enabled == 2 ? 4096 : 0;            // test mode: keep parking after the release until TMEM is full
   for (int it = 0;; ++it) {
     if (threadIdx.x == 0) {
       int code = 0;
-      if (ld_acquire_u32(bar) >= target) code = 2;
-      else if (st.tm_count < TM_SLOTS && st.seq_left > 0 && mbar_test(&m.full[st.s], st.ph)) code = 1;
+      const bool can = st.tm_count < TM_SLOTS && st.seq_left > 0;
+      if (can && mbar_test(&m.full[st.s], st.ph)) code = 1;
+      else if (tab.released == target && (!can || --patience < 0)) code = 2;
+      if (code == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // the poller's acquire, made ours before the CTA barrier
       tab.code[it & 1] = code;
     }
     cons_sync();
@@ -128,9 +137,48 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Strea
   }
 }
 
-// One k-phase of one matrix on the consumer side: the first min(tm_count, items) items of the phase are parked in
-// TMEM, the rest comes through the ring.  Ring tiles and TMEM tiles are visited alternately so that ring stages are
-// handed back to the producer from the first microsecond of the phase.
+// the poller warp (one lane): for every barrier the consumers arrive at, wait for the grid and report it
+__device__ __forceinline__ void barrier_poller(const unsigned* bar, StreamTab& tab) {
+  unsigned done = 0;
+  for (;;) {
+    unsigned t;
+    while ((t = tab.arrived) == done) { }
+    if (t == 0xffffffffu) return;
+    while (ld_acquire_u32(bar) < t) { }
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    tab.released = t;
+    done = t;
+  }
+}
+
+// One k-phase of one matrix on the consumer side.  The first n_tm = min(tm_count, items) items of the phase are parked
+// in TMEM, the rest comes through the ring.  Every warp runs two tile streams with their own accumulators:
+//   ring stream : tiles from the one that contains item n_tm onwards -- taken whenever the ring-front stage is full,
+//                 so stages go back to the producer as early as possible and the HBM stream never stalls on us;
+//   TMEM stream : tiles [0, ts) -- read back (tcgen05.ld) in the slack while the ring-front stage is still in flight.
+// The parked head of the straddled tile is folded into the ring accumulator first.  A tile is always accumulated in
+// k order in one accumulator, so the result does not depend on how many stages were parked or on the interleaving.
+// Warps run decoupled inside a phase (each owns a K slice of every stage) and meet again at the caller's cons_sync.
+__device__ __forceinline__ void mma_item(float (&c)[4], const uint32_t (&w)[32], const __half* xp, bool xok, int nch) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (ch < nch) {
+      const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
+      mma_16816(c, w[ch * 8 + 0], w[ch * 8 + 4], w[ch * 8 + 1], w[ch * 8 + 5], xv.x, xv.y);
+      mma_16816(c, w[ch * 8 + 2], w[ch * 8 + 6], w[ch * 8 + 3], w[ch * 8 + 7], xv.z, xv.w);
+    }
+  }
+}
+__device__ __forceinline__ void flush_tile(float* p, const float (&c)[4], int g, int t, bool add) {
+  if (add) {
+    p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
+    p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
+  } else {
+    p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
+    p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+  }
+}
+
 __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, int k0, int KP, int KS, int r0, int r1, int vlo,
                                               int vhi, const GvSmem& m, int B, int stages) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,56 +198,63 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
       p[g * 8 + 2 * t] = 0.f; p[g * 8 + 2 * t + 1] = 0.f; p[(g + 8) * 8 + 2 * t] = 0.f; p[(g + 8) * 8 + 2 * t + 1] = 0.f;
     }
   }
-  const int nvt = thi - tlo;
-  const int n_items = nvt * nks;
+  const int n_items = (thi - tlo) * nks;
   const int n_tm = min(st.tm_count, n_items);
-  const int ts = n_tm / nks;                      // tiles [0, ts) come from TMEM only; tile ts starts in TMEM (maybe 0 items)
+  const int ts = n_tm / nks;                      // tiles [0, ts) come from TMEM only; tile ts starts in TMEM (maybe with 0 items)
+  const int na = ts * nks;                        // items of the TMEM stream
   const __half* xbase = m.xs + g * (KP + XS_PAD) + warp * ksw + t * 8;
-  int ta = 0, tr = ts;
-  while (tr < nvt || ta < ts) {
-    int vt;
-    if (tr < nvt && (ta >= ts || ((tr - ts) <= ta))) vt = tr++;
-    else vt = ta++;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < nks; ++j) {
-      const int i = vt * nks + j;
-      const __half* xp = xbase + j * KS;
-      if (i < n_tm) {
-        uint32_t rr[32];
-        tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + i) & (TM_SLOTS - 1)) * 32u, rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nch) {
-            const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
-            mma_16816(c, rr[ch * 8 + 0], rr[ch * 8 + 4], rr[ch * 8 + 1], rr[ch * 8 + 5], xv.x, xv.y);
-            mma_16816(c, rr[ch * 8 + 2], rr[ch * 8 + 6], rr[ch * 8 + 3], rr[ch * 8 + 7], xv.z, xv.w);
-          }
-        }
-      } else {
-        mbar_wait(&m.full[st.s], st.ph);
-        const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
-        const __half* wb = wa + 8 * wpitch;
-#pragma unroll 4
-        for (int ch = 0; ch < nch; ++ch) {
-          const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
-          const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
-          const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
-          mma_16816(c, a.x, b.x, a.y, b.y, xv.x, xv.y);
-          mma_16816(c, a.z, b.z, a.w, b.w, xv.z, xv.w);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&m.empty[st.s]);
-        stream_ring_advance(st, stages);
-      }
+  float* pbase = m.s_part + (static_cast<size_t>(tlo) * GV_WARPS + warp) * (GV_TILE * 8);
+  const bool add = k0 > 0;
+  float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t w[32];
+  // parked head of the straddled tile -> ring accumulator
+  for (int i = na; i < n_tm; ++i) {
+    tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + i) & (TM_SLOTS - 1)) * 32u, w);
+    tmem_ld_wait();
+    mma_item(cb, w, xbase + (i - na) * KS, xok, nch);
+  }
+  int ia = 0, ib = n_tm;
+  while (ia < na || ib < n_items) {
+    bool ring;
+    if (ib >= n_items) ring = false;
+    else if (ia >= na) ring = true;
+    else {
+      int ok = 0;
+      if (lane == 0) ok = mbar_test(&m.full[st.s], st.ph) ? 1 : 0;
+      ring = __shfl_sync(0xffffffffu, ok, 0) != 0;
     }
-    float* p = m.s_part + (static_cast<size_t>(tlo + vt) * GV_WARPS + warp) * (GV_TILE * 8);
-    if (k0 > 0) {
-      p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
-      p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
+    if (ring) {
+      const int j = ib % nks;
+      mbar_wait(&m.full[st.s], st.ph);
+      const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
+      const __half* wb = wa + 8 * wpitch;
+      const __half* xp = xbase + j * KS;
+#pragma unroll 2
+      for (int ch = 0; ch < nch; ++ch) {
+        const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+        const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
+        mma_16816(cb, a.x, b.x, a.y, b.y, xv.x, xv.y);
+        mma_16816(cb, a.z, b.z, a.w, b.w, xv.z, xv.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&m.empty[st.s]);
+      stream_ring_advance(st, stages);
+      if (j == nks - 1) {
+        flush_tile(pbase + static_cast<size_t>(ib / nks) * (GV_WARPS * GV_TILE * 8), cb, g, t, add);
+        cb[0] = cb[1] = cb[2] = cb[3] = 0.f;
+      }
+      ++ib;
     } else {
-      p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
-      p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+      const int j = ia % nks;
+      tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + ia) & (TM_SLOTS - 1)) * 32u, w);
+      tmem_ld_wait();
+      mma_item(ca, w, xbase + j * KS, xok, nch);
+      if (j == nks - 1) {
+        flush_tile(pbase + static_cast<size_t>(ia / nks) * (GV_WARPS * GV_TILE * 8), ca, g, t, add);
+        ca[0] = ca[1] = ca[2] = ca[3] = 0.f;
+      }
+      ++ia;
     }
   }
   st.tm_head = (st.tm_head + n_tm) & (TM_SLOTS - 1);
@@ -265,6 +320,11 @@ __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 32 + k] = t;
   }
+}
+
+__device__ __forceinline__ void stamp_val(const MegaParams& p, int l, int k, unsigned long long v) {
+  if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 32 + k] = v;
 }
 
 // Per-step attention control block of this CTA's (fixed) work item: everything that would otherwise be a chain of
@@ -635,7 +695,7 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
     if (PRO == 1) stage_x_rmsnorm(m.xs, xin, ldx, p.B, K, gm, p.eps, m.s_red);
     else stage_x_plain(m.xs, xin, ldx, p.B, k0, KP);
     cons_sync();
-    if (dk >= 0 && k0 == 0) stamp(p, dl, dk);
+    if (dk >= 0 && k0 == 0) { stamp(p, dl, dk); stamp_val(p, dl, 25 + (dk - 10) / 2, static_cast<unsigned long long>(st.tm_count)); }
     // the staged row pitch is KP + XS_PAD: consume_phase derives it from KP
     consume_phase(st, tab, k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages);
   }
@@ -644,7 +704,7 @@ __device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, c
   gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
 }
 
-__global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve with the largest stage (KS = 1024) and the reserved activation capacity
   GvSmem m;
@@ -661,7 +721,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   __shared__ volatile int s_gate;     // layer index + 1 whose attention loads have been issued (consumers -> producer)
   __shared__ uint32_t s_tmem;
   __shared__ StreamTab s_tab;
-  if (threadIdx.x == 0) s_gate = 0;
+  if (threadIdx.x == 0) { s_gate = 0; s_tab.arrived = 0; s_tab.released = 0; }
   if (p.tm_relay && threadIdx.x < 32) tmem_alloc(&s_tmem, TM_COLS);   // whole TMEM: one CTA per SM by shared-memory footprint
   tc_fence_before();
   gv_init_barriers(m, p.stages);
@@ -681,6 +741,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
     }
   }
 
+  if (threadIdx.x >= GV_THREADS) {
+    // ===================== poller warp: watches the grid barrier word while the consumers park stages =====================
+    if (p.tm_relay && threadIdx.x == GV_THREADS) barrier_poller(p.gbar, s_tab);
+    return;
+  }
   if (threadIdx.x >= GV_CONS) {
     // ===================== producer warp: the whole step's weight stream =====================
     int s = 0;
@@ -863,6 +928,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_step_kernel(const __grid
   if (blockIdx.x == 0) finalize_step(p, ncta);
   // exit protocol: the last CTA to leave resets the barrier counters for the next launch
   cons_sync();
+  if (threadIdx.x == 0) s_tab.arrived = 0xffffffffu;    // poller warp: quit
   if (p.tm_relay && threadIdx.x < 32) {
     __syncwarp();
     tmem_dealloc(s_tmem, TM_COLS);
@@ -954,34 +1020,8 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.part_o = a.part_o; p.part_ml = a.part_ml; p.counters = a.counters; p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
   p.logits_out = a.logits_out; p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
-  {
-    static int pf = -1;
-    if (pf < 0) {
-      const char* e = getenv("TRACE_B200_PF_AHEAD");
-      pf = (e != nullptr && atoi(e) >= 0 && atoi(e) <= 64) ? atoi(e) : 0;
-    }
-    p.pf_ahead = pf;
-    static int gap_kb = -1, attn_kb = -1;
-    if (gap_kb < 0) {
-      const char* e1 = getenv("TRACE_B200_PF_GAP_KB");
-      const char* e2 = getenv("TRACE_B200_PF_ATTN_KB");
-      gap_kb = (e1 != nullptr && atoi(e1) >= 0 && atoi(e1) <= 4096) ? atoi(e1) : 0;
-      attn_kb = (e2 != nullptr && atoi(e2) >= 0 && atoi(e2) <= 4096) ? atoi(e2) : 0;
-    }
-    p.pf_gap_kb = gap_kb;
-    p.pf_attn_kb = attn_kb;
-  }
-  {
-    static int relay = -1, gate = -1;
-    if (relay < 0) {
-      const char* e = getenv("TRACE_B200_TM_RELAY");
-      relay = (e != nullptr) ? (atoi(e) != 0) : 1;
-      const char* g = getenv("TRACE_B200_GATE_MODE");
-      gate = (g != nullptr && atoi(g) >= 0 && atoi(g) <= 2) ? atoi(g) : (relay ? 2 : 1);
-    }
-    p.tm_relay = relay;
-    p.gate_mode = gate;
-  }
+  p.pf_ahead = a.pf_ahead; p.pf_gap_kb = a.pf_gap_kb; p.pf_attn_kb = a.pf_attn_kb;
+  p.tm_relay = a.tm_relay; p.gate_mode = a.gate_mode;
   p.dbg = a.dbg;
   int kpks[10];
   size_t smem = 0;
@@ -997,7 +1037,7 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
     cached = smem;
   }
   // every CTA must be resident at once (grid barriers): one CTA per SM by shared-memory footprint, grid = #SMs
-  decode_step_kernel<<<a.num_sms, GV_THREADS, smem, stream>>>(p);
+  decode_step_kernel<<<a.num_sms, MG_THREADS, smem, stream>>>(p);
   TB_LAUNCH_OK();
   return 0;
 }
