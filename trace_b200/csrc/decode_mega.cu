@@ -683,27 +683,49 @@ __device__ __forceinline__ void prefetch_next_rows(const __half* W, int K, int N
     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-// one GEMV phase on the consumer side: stage activations (k-phases), consume, epilogue
-template <int PRO, int EPI>
-__device__ __forceinline__ void gemv_phase_cons(const MegaParams& p, GvSmem m, const __half* xin, int ldx, __half* out, int ldo,
-                                                int N, int K, int KP, int KS, const GammaRegs& gm, Stream& st, const StreamTab& tab,
-                                                int dl = 0, int dk = -1) {
-  int r0, r1;
-  cta_rows(N, r0, r1);
-  for (int k0 = 0; k0 < K; k0 += KP) {
-    if (k0 > 0) cons_sync();
-    if (PRO == 1) stage_x_rmsnorm(m.xs, xin, ldx, p.B, K, gm, p.eps, m.s_red);
-    else stage_x_plain(m.xs, xin, ldx, p.B, k0, KP);
-    cons_sync();
-    if (dk >= 0 && k0 == 0) { stamp(p, dl, dk); stamp_val(p, dl, 25 + (dk - 10) / 2, static_cast<unsigned long long>(st.tm_count)); }
-    // the staged row pitch is KP + XS_PAD: consume_phase derives it from KP
-    consume_phase(st, tab, k0, KP, KS, r0, r1, r0, r1, m, p.B, p.stages);
+// Phase geometry, indexed by phase type (0 qkv, 1 o, 2 gate/up, 3 down, 4 head).  The kernel body is ONE loop over the
+// 4*layers+1 phases of the step with one copy of every building block: the step's code (~350 KB of SASS when every
+// phase had its own inlined copy) is re-executed for each of the 32 layers, and anything that does not fit the
+// instruction cache is re-fetched from L2 32 times per token in exactly the latency-bound sections between the
+// streaming loops.
+struct PhaseGeo { int N, K, KP, KS; };
+__device__ __forceinline__ PhaseGeo phase_geo(const MegaParams& p, int type) {
+  PhaseGeo g;
+  switch (type) {
+    case 0: g.N = p.qkvw; g.K = p.H; g.KP = p.kp_qkv; g.KS = p.ks_qkv; break;
+    case 1: g.N = p.H; g.K = p.qd; g.KP = p.kp_o; g.KS = p.ks_o; break;
+    case 2: g.N = 2 * p.ffn; g.K = p.H; g.KP = p.kp_gu; g.KS = p.ks_gu; break;
+    case 3: g.N = p.H; g.K = p.ffn; g.KP = p.kp_dn; g.KS = p.ks_dn; break;
+    default: g.N = p.head_rows; g.K = p.H; g.KP = p.kp_hd; g.KS = p.ks_hd; break;
   }
-  cons_sync();
-  if (dk >= 0) stamp(p, dl, dk + 1);
-  gemv_epilogue<EPI>(m, r0, r1, p.B, out, ldo);
+  return g;
+}
+__device__ __forceinline__ const __half* phase_weights(const MegaParams& p, const MegaLayer& L, int type) {
+  return type == 0 ? L.qkv_w : type == 1 ? L.o_w : type == 2 ? L.gateup_w : type == 3 ? L.down_w : p.head_w;
 }
 
+// epilogue of a layer phase (256 consumer threads, after the partials are complete): epi 0 store, 1 residual add in
+// place, 2 SwiGLU pairs
+__device__ __forceinline__ void phase_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo, int epi) {
+  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+  for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+    const float v = gemv_out(m.s_part, idx);
+    const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
+    const float partner = __shfl_xor_sync(0xffffffffu, v, 8);
+    if (epi == 2) {
+      if ((row & 1) == 0 && n < B && row < r1) __stcg(out + static_cast<size_t>(n) * ldo + (row >> 1), __float2half_rn(silu_f(v) * partner));
+    } else if (n < B && row < r1) {
+      __half* o = out + static_cast<size_t>(n) * ldo + row;
+      __stcg(o, __float2half_rn(epi == 1 ? v + __half2float(__ldcg(o)) : v));
+    }
+  }
+}
+
+__device__ __noinline__ void grid_sync_shared(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, const GvSmem& m, int stages) {
+  grid_sync(bar, target, st, tab, m, stages);
+}
+
+template <int NB>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve with the largest stage (KS = 1024) and the reserved activation capacity
@@ -721,25 +743,24 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
   __shared__ volatile int s_gate;     // layer index + 1 whose attention loads have been issued (consumers -> producer)
   __shared__ uint32_t s_tmem;
   __shared__ StreamTab s_tab;
+  __shared__ int s_hlo[GV_MAXB], s_hhi[GV_MAXB];
   if (threadIdx.x == 0) { s_gate = 0; s_tab.arrived = 0; s_tab.released = 0; }
   if (p.tm_relay && threadIdx.x < 32) tmem_alloc(&s_tmem, TM_COLS);   // whole TMEM: one CTA per SM by shared-memory footprint
+  // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
+  // late producer warp must not see the new values or it would stream rows that nobody consumes)
+  if (threadIdx.x < GV_MAXB) {
+    int lo = 0, hi = 0;
+    if (threadIdx.x < p.B) head_range(p.st.heads[threadIdx.x], p.vocab, lo, hi);
+    s_hlo[threadIdx.x] = lo;
+    s_hhi[threadIdx.x] = hi;
+  }
   tc_fence_before();
   gv_init_barriers(m, p.stages);
   tc_fence_after();
   const int ncta = gridDim.x;
-  // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
-  // late producer warp must not see the new values or it would stream rows that nobody consumes)
-  int hlo[GV_MAXB], hhi[GV_MAXB];
   int ulo = 0x7fffffff, uhi = 0;
-#pragma unroll
-  for (int b = 0; b < GV_MAXB; ++b) {
-    hlo[b] = hhi[b] = 0;
-    if (b < p.B) {
-      head_range(p.st.heads[b], p.vocab, hlo[b], hhi[b]);
-      ulo = min(ulo, hlo[b]);
-      uhi = max(uhi, hhi[b]);
-    }
-  }
+  for (int b = 0; b < p.B; ++b) { ulo = min(ulo, s_hlo[b]); uhi = max(uhi, s_hhi[b]); }
+  const int nseq = p.layers * 4 + 1;            // phases of the step: 4 per layer + head
 
   if (threadIdx.x >= GV_THREADS) {
     // ===================== poller warp: watches the grid barrier word while the consumers park stages =====================
@@ -750,58 +771,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
     // ===================== producer warp: the whole step's weight stream =====================
     int s = 0;
     uint32_t ph = 0;
-    int r0, r1;
-    // this CTA's attention work item (fixed for the step): prefetch its K/V rows into L2 while the QKV weights stream
-    const int items = p.B * p.kvh * p.nsplit;
-    const int my_it = blockIdx.x < items ? static_cast<int>(blockIdx.x) : -1;
-    int a_kv = 0, a_start = 0, a_end = 0;
-    const int32_t* a_table = nullptr;
-    if (my_it >= 0) {
-      const int split = my_it % p.nsplit, b = my_it / (p.nsplit * p.kvh);
-      a_kv = (my_it / p.nsplit) % p.kvh;
-      const int t = p.st.pos[b];
-      int chunk = (t + p.nsplit - 1) / p.nsplit;
-      chunk = (chunk + 31) & ~31;
-      a_start = split * chunk;
-      a_end = min(a_start + chunk, t);
-      a_table = p.block_table + static_cast<size_t>(p.st.slot_ids[b]) * p.max_pages;
-    }
-    for (int l = 0; l < p.layers; ++l) {
-      const MegaLayer L = p.L[l];
-      if (p.pf_ahead > 0 && my_it >= 0 && items <= static_cast<int>(gridDim.x)) {
-        // pages are contiguous per (page, kv head): [page_size][128] halves
-        for (int k = a_start + (threadIdx.x & 31) * p.page_size - (a_start % p.page_size); k < a_end; k += 32 * p.page_size) {
-          const int lo = max(k, a_start), hi = min(k + p.page_size, a_end);
-          if (lo < hi) {
-            const size_t off = ((static_cast<size_t>(a_table[lo / p.page_size]) * p.kvh + a_kv) * p.page_size + lo % p.page_size) * MG_HD;
-            bulk_prefetch_l2(L.k_pool + off, static_cast<uint32_t>(hi - lo) * MG_HD * 2);
-            bulk_prefetch_l2(L.v_pool + off, static_cast<uint32_t>(hi - lo) * MG_HD * 2);
-          }
-        }
-      }
-      cta_rows(p.qkvw, r0, r1);
-      gemv_producer(L.qkv_w, p.H, p.kp_qkv, p.ks_qkv, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
-      if (p.gate_mode == 1) {
+    for (int seq = 0; seq < nseq; ++seq) {
+      const int type = seq == nseq - 1 ? 4 : (seq & 3), l = seq >> 2;
+      const MegaLayer L = p.L[type == 4 ? 0 : l];
+      if (type == p.gate_mode && type != 0) {       // gate_mode 1: before the O weights, 2: before the gate/up weights
         if ((threadIdx.x & 31) == 0)
           while (s_gate < l + 1) { }
         __syncwarp();
       }
-      cta_rows(p.H, r0, r1);
-      gemv_producer(L.o_w, p.qd, p.kp_o, p.ks_o, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
-      if (p.gate_mode == 2) {
-        if ((threadIdx.x & 31) == 0)
-          while (s_gate < l + 1) { }
-        __syncwarp();
-      }
-      cta_rows(2 * p.ffn, r0, r1);
-      gemv_producer(L.gateup_w, p.H, p.kp_gu, p.ks_gu, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
-      cta_rows(p.H, r0, r1);
-      gemv_producer(L.down_w, p.ffn, p.kp_dn, p.ks_dn, r0, r1, r0, r1, m, p.stages, s, ph, p.pf_ahead);
+      const PhaseGeo g = phase_geo(p, type);
+      int r0, r1;
+      cta_rows(g.N, r0, r1);
+      // head: only the rows some batch row decodes from (heads[] was written by the previous step)
+      const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
+      if (vlo < vhi) gemv_producer(phase_weights(p, L, type), g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, p.pf_ahead);
     }
-    // head: only the rows some batch row decodes from (heads[] was written by the previous step)
-    cta_rows(p.head_rows, r0, r1);
-    const int vlo = max(ulo, r0), vhi = min(uhi, r1);
-    if (vlo < vhi) gemv_producer(p.head_w, p.H, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.stages, s, ph, p.pf_ahead);
     return;
   }
 
@@ -811,120 +795,112 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
   attn_ctl_init(p, ctl);
   unsigned target = 0;
   // ---- weight-stream bookkeeping: items per phase type for THIS CTA (must mirror the producer's enumeration) ----
-  int hd_r0, hd_r1;
-  cta_rows(p.head_rows, hd_r0, hd_r1);
-  const int hd_vlo = max(ulo, hd_r0), hd_vhi = min(uhi, hd_r1);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 5) {
+    const PhaseGeo g = phase_geo(p, threadIdx.x);
     int r0, r1;
-    cta_rows(p.qkvw, r0, r1);
-    s_tab.cnt[0] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.H / p.ks_qkv);
-    cta_rows(p.H, r0, r1);
-    s_tab.cnt[1] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.qd / p.ks_o);
-    s_tab.cnt[3] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.ffn / p.ks_dn);
-    cta_rows(2 * p.ffn, r0, r1);
-    s_tab.cnt[2] = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (p.H / p.ks_gu);
-    s_tab.cnt[4] = hd_vlo < hd_vhi ? ((hd_vhi - 1 - hd_r0) / GV_TILE - (hd_vlo - hd_r0) / GV_TILE + 1) * (p.H / p.ks_hd) : 0;
-    s_tab.ks[0] = p.ks_qkv; s_tab.ks[1] = p.ks_o; s_tab.ks[2] = p.ks_gu; s_tab.ks[3] = p.ks_dn; s_tab.ks[4] = p.ks_hd;
+    cta_rows(g.N, r0, r1);
+    int nt = (r1 - r0 + GV_TILE - 1) / GV_TILE;
+    if (threadIdx.x == 4) {
+      const int vlo = max(ulo, r0), vhi = min(uhi, r1);
+      nt = vlo < vhi ? (vhi - 1 - r0) / GV_TILE - (vlo - r0) / GV_TILE + 1 : 0;
+    }
+    s_tab.cnt[threadIdx.x] = nt * (g.K / g.KS);
+    s_tab.ks[threadIdx.x] = g.KS;
   }
   cons_sync();
   Stream st;
   st.s = 0; st.ph = 0; st.tm_head = 0; st.tm_count = 0;
-  st.seq_end = p.layers * 4 + 1;
+  st.seq_end = nseq;
   st.seq = 0; st.seq_left = s_tab.cnt[0];
   stream_skip_empty(st, s_tab);
   st.enabled = p.tm_relay;
   st.tm_base = p.tm_relay ? s_tmem + (static_cast<uint32_t>(32 * ((threadIdx.x >> 5) & 3)) << 16) + static_cast<uint32_t>((threadIdx.x >> 7) * (TM_SLOTS * 32)) : 0u;
-  for (int l = 0; l < p.layers; ++l) {
+
+  for (int seq = 0; seq < nseq; ++seq) {
+    const int type = seq == nseq - 1 ? 4 : (seq & 3), l = type == 4 ? p.layers - 1 : (seq >> 2);
     const MegaLayer L = p.L[l];
-    GammaRegs gm = load_gamma(L.ln1, p.H);                                    // weights: issued before the barrier
-    attn_prefetch(p, L, *ctl);
-    if (l > 0) prefetch_next_rows(L.qkv_w, p.H, p.qkvw, GV_TILE, p.pf_gap_kb);
-    if (l > 0) grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                     // residual stream complete
-    stamp(p, l, 0);
-    gemv_phase_cons<1, 0>(p, m, p.x, p.H, p.qkv, p.qkvw, p.qkvw, p.H, p.kp_qkv, p.ks_qkv, gm, st, s_tab, l, 10);
-    stamp(p, l, 1);
-    prefetch_next_rows(L.o_w, p.qd, p.H, GV_TILE, p.pf_attn_kb);               // the attention gap is long: O + start of gate/up
-    prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, 0, p.pf_attn_kb);
-    grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                                // q, k, v complete
-    stamp(p, l, 2);
-    {
-      if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, &s_gate);
-      else if (threadIdx.x == 0) s_gate = l + 1;
-    }
-    stamp(p, l, 3);
-    grid_sync(p.gbar, target, st, s_tab, m, p.stages);                                                // attention output complete
-    stamp(p, l, 4);
-    gemv_phase_cons<0, 1>(p, m, p.attn, p.qd, p.x, p.H, p.H, p.qd, p.kp_o, p.ks_o, gm, st, s_tab, l, 12);
-    stamp(p, l, 5);
-    gm = load_gamma(L.ln2, p.H);
-    prefetch_next_rows(L.gateup_w, p.H, 2 * p.ffn, GV_TILE + (p.pf_attn_kb * 1024) / (p.H * 2), p.pf_gap_kb);
-    grid_sync(p.gbar, target, st, s_tab, m, p.stages);
-    stamp(p, l, 6);
-    gemv_phase_cons<1, 2>(p, m, p.x, p.H, p.act, p.ffn, 2 * p.ffn, p.H, p.kp_gu, p.ks_gu, gm, st, s_tab, l, 14);
-    stamp(p, l, 7);
-    prefetch_next_rows(L.down_w, p.ffn, p.H, 4, p.pf_gap_kb);
-    grid_sync(p.gbar, target, st, s_tab, m, p.stages);
-    stamp(p, l, 8);
-    gemv_phase_cons<0, 1>(p, m, p.act, p.ffn, p.x, p.H, p.H, p.ffn, p.kp_dn, p.ks_dn, gm, st, s_tab, l, 16);
-    stamp(p, l, 9);
-  }
-  const GammaRegs gmf = load_gamma(p.final_norm, p.H);
-  grid_sync(p.gbar, target, st, s_tab, m, p.stages);
-  // ---- heads: final RMSNorm + logits of the active ranges + argmax candidates ----
-  {
+    const PhaseGeo g = phase_geo(p, type);
+    const bool pro = (type != 1 && type != 3);                                  // RMSNorm fused into the staging
+    // weights needed right after the barrier: issued before it so that their latency hides behind the wait
+    GammaRegs gm;
+    if (pro) gm = load_gamma(type == 0 ? L.ln1 : type == 2 ? L.ln2 : p.final_norm, p.H);
+    if (type == 0) attn_prefetch(p, L, *ctl);
+    if (seq > 0) grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);      // the phase's input vector is complete
+    stamp(p, l, type * 2 + (type > 0 ? 2 : 0));
     int r0, r1;
-    cta_rows(p.head_rows, r0, r1);
-    const int vlo = max(ulo, r0), vhi = min(uhi, r1);
-    const int n = threadIdx.x & 7;
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
-    __shared__ float s_cv[GV_WARPS][8];
-    __shared__ int s_ci[GV_WARPS][8];
+    cta_rows(g.N, r0, r1);
+    const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
+    const __half* xin = type == 1 ? p.attn : type == 3 ? p.act : p.x;
     if (vlo < vhi) {
-      stage_x_rmsnorm(m.xs, p.x, p.H, p.B, p.H, gmf, p.eps, m.s_red);
+      for (int k0 = 0; k0 < g.K; k0 += g.KP) {
+        if (k0 > 0) cons_sync();
+        if (pro) stage_x_rmsnorm_nb<NB>(m.xs, xin, g.K, p.B, g.K, gm, p.eps, m.s_red);
+        else stage_x_plain(m.xs, xin, g.K, p.B, k0, g.KP);
+        cons_sync();
+        if (k0 == 0) { stamp(p, l, 10 + type * 2); stamp_val(p, l, 25 + type, static_cast<unsigned long long>(st.tm_count)); }
+        consume_phase(st, s_tab, k0, g.KP, g.KS, r0, r1, vlo, vhi, m, p.B, p.stages);
+      }
       cons_sync();
-      consume_phase(st, s_tab, 0, p.kp_hd, p.ks_hd, r0, r1, vlo, vhi, m, p.B, p.stages);
+      stamp(p, l, 11 + type * 2);
+    }
+    if (type < 4) {
+      __half* out = type == 0 ? p.qkv : type == 2 ? p.act : p.x;
+      phase_epilogue(m, r0, r1, p.B, out, type == 0 ? p.qkvw : type == 2 ? p.ffn : p.H, type == 2 ? 2 : (type == 0 ? 0 : 1));
+      stamp(p, l, type * 2 + (type > 0 ? 3 : 1));
+      if (type == 0) {
+        grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);               // q, k, v complete
+        stamp(p, l, 2);
+        if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, &s_gate);
+        else if (threadIdx.x == 0) s_gate = l + 1;
+        stamp(p, l, 3);
+      }
+    } else {
+      // ---- heads: logits of the active ranges (fp16-rounded like the reference's fp16 GEMM) + argmax candidates ----
+      const int n = threadIdx.x & 7;
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+      __shared__ float s_cv[GV_WARPS][8];
+      __shared__ int s_ci[GV_WARPS][8];
+      if (vlo < vhi) {
+        const int lo = s_hlo[n], hi = s_hhi[n];
+        for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+          const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+          float v = __half2float(__float2half_rn(gemv_out(m.s_part, idx)));
+          const bool act = (n < p.B) && r < r1 && r >= lo && r < hi;
+          if (!act) v = -INFINITY;
+          if (p.logits_out != nullptr && n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = v;
+          if (act && (v > bv || (v == bv && r < bi))) { bv = v; bi = r; }
+        }
+      } else if (p.logits_out != nullptr) {
+        for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
+          const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+          if (n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
       cons_sync();
-      int lo = 0, hi = 0;
+      if (threadIdx.x < p.B) {
+        float v = s_cv[0][threadIdx.x];
+        int i = s_ci[0][threadIdx.x];
 #pragma unroll
-      for (int b = 0; b < GV_MAXB; ++b) if (b == n) { lo = hlo[b]; hi = hhi[b]; }
-      for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-        const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
-        float v = __half2float(__float2half_rn(gemv_out(m.s_part, idx)));
-        const bool act = (n < p.B) && r < r1 && r >= lo && r < hi;
-        if (!act) v = -INFINITY;
-        if (p.logits_out != nullptr && n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = v;
-        if (act && (v > bv || (v == bv && r < bi))) { bv = v; bi = r; }
+        for (int w = 1; w < GV_WARPS; ++w) {
+          const float ov = s_cv[w][threadIdx.x];
+          const int oi = s_ci[w][threadIdx.x];
+          if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        __stcg(p.cand_val + threadIdx.x * ncta + blockIdx.x, v);
+        __stcg(p.cand_idx + threadIdx.x * ncta + blockIdx.x, i);
       }
-    } else if (p.logits_out != nullptr) {
-      for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-        const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
-        if (n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = -INFINITY;
-      }
-    }
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
-    cons_sync();
-    if (threadIdx.x < p.B) {
-      float v = s_cv[0][threadIdx.x];
-      int i = s_ci[0][threadIdx.x];
-#pragma unroll
-      for (int w = 1; w < GV_WARPS; ++w) {
-        const float ov = s_cv[w][threadIdx.x];
-        const int oi = s_ci[w][threadIdx.x];
-        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-      }
-      __stcg(p.cand_val + threadIdx.x * ncta + blockIdx.x, v);
-      __stcg(p.cand_idx + threadIdx.x * ncta + blockIdx.x, i);
     }
   }
-  grid_sync(p.gbar, target, st, s_tab, m, p.stages);
+  grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);
   if (blockIdx.x == 0) finalize_step(p, ncta);
   // exit protocol: the last CTA to leave resets the barrier counters for the next launch
   cons_sync();
@@ -1031,13 +1007,18 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.kp_qkv = kpks[0]; p.ks_qkv = kpks[1]; p.kp_o = kpks[2]; p.ks_o = kpks[3]; p.kp_gu = kpks[4]; p.ks_gu = kpks[5];
   p.kp_dn = kpks[6]; p.ks_dn = kpks[7]; p.kp_hd = kpks[8]; p.ks_hd = kpks[9];
   TB_CHECK(a.heads == a.kvh * MG_G && a.qd == a.heads * MG_HD, "fused decode step is specialised for 128-dim heads, 4 q heads per kv head");
-  static size_t cached = 0;
-  if (smem > cached) {
-    TB_CUDA(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    cached = smem;
-  }
   // every CTA must be resident at once (grid barriers): one CTA per SM by shared-memory footprint, grid = #SMs
-  decode_step_kernel<<<a.num_sms, MG_THREADS, smem, stream>>>(p);
+  auto launch = [&](auto kern) -> int {
+    TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<a.num_sms, MG_THREADS, smem, stream>>>(p);
+    return 0;
+  };
+  int rc;
+  if (a.B == 1) rc = launch(decode_step_kernel<1>);
+  else if (a.B == 2) rc = launch(decode_step_kernel<2>);
+  else if (a.B <= 4) rc = launch(decode_step_kernel<4>);
+  else rc = launch(decode_step_kernel<8>);
+  if (rc) return rc;
   TB_LAUNCH_OK();
   return 0;
 }

@@ -14,7 +14,8 @@ import torch
 
 from . import synth
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrace_b200.so")
+# TRACE_B200_LIB selects another in-tree build of the same ABI (A/B runs of two kernel versions on one box)
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("TRACE_B200_LIB", "libtrace_b200.so"))
 _lib = None
 
 EXPORTS = [
