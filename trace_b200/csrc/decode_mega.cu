@@ -21,6 +21,7 @@ namespace {
 
 constexpr int MG_G = 4;       // query heads per kv head
 constexpr int MG_HD = 128;
+constexpr int MG_MAX_LAYERS = 48;
 
 // ---- grid barrier (consumer warps only; the producer warp never synchronises with anything but its ring) ----
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -125,8 +126,8 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Strea
     if (threadIdx.x == 0) {
       int code = 0;
       const bool can = st.tm_count < TM_SLOTS && st.seq_left > 0;
-      if (can && mbar_test(&m.full[st.s], st.ph)) code = 1;
-      else if (tab.released == target && (!can || --patience < 0)) code = 2;
+      if (tab.released == target && (!can || --patience < 0)) code = 2;   // leave as soon as the grid is through
+      else if (can && mbar_test(&m.full[st.s], st.ph)) code = 1;
       if (code == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // the poller's acquire, made ours before the CTA barrier
       tab.code[it & 1] = code;
     }
@@ -229,7 +230,7 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
       const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
       const __half* wb = wa + 8 * wpitch;
       const __half* xp = xbase + j * KS;
-#pragma unroll 2
+#pragma unroll 4
       for (int ch = 0; ch < nch; ++ch) {
         const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
         const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
@@ -744,6 +745,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
   __shared__ uint32_t s_tmem;
   __shared__ StreamTab s_tab;
   __shared__ int s_hlo[GV_MAXB], s_hhi[GV_MAXB];
+  // the layer pointer table, read once: a dependent L2 round trip per phase (producer: before the first copy of the phase;
+  // consumers: before the gamma prefetch) would sit on the critical path 129 times per token
+  __shared__ MegaLayer s_layers[MG_MAX_LAYERS];
+  for (int i = threadIdx.x; i < p.layers * static_cast<int>(sizeof(MegaLayer) / 8); i += MG_THREADS)
+    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.L)[i];
   if (threadIdx.x == 0) { s_gate = 0; s_tab.arrived = 0; s_tab.released = 0; }
   if (p.tm_relay && threadIdx.x < 32) tmem_alloc(&s_tmem, TM_COLS);   // whole TMEM: one CTA per SM by shared-memory footprint
   // active-head row ranges: read ONCE, before anything of this step can rewrite heads[] (CTA 0's finalize does, and a
@@ -773,7 +779,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
     uint32_t ph = 0;
     for (int seq = 0; seq < nseq; ++seq) {
       const int type = seq == nseq - 1 ? 4 : (seq & 3), l = seq >> 2;
-      const MegaLayer L = p.L[type == 4 ? 0 : l];
+      const MegaLayer& L = s_layers[type == 4 ? 0 : l];
       if (type == p.gate_mode && type != 0) {       // gate_mode 1: before the O weights, 2: before the gate/up weights
         if ((threadIdx.x & 31) == 0)
           while (s_gate < l + 1) { }
@@ -818,7 +824,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
 
   for (int seq = 0; seq < nseq; ++seq) {
     const int type = seq == nseq - 1 ? 4 : (seq & 3), l = type == 4 ? p.layers - 1 : (seq >> 2);
-    const MegaLayer L = p.L[l];
+    const MegaLayer& L = s_layers[l];
     const PhaseGeo g = phase_geo(p, type);
     const bool pro = (type != 1 && type != 3);                                  // RMSNorm fused into the staging
     // weights needed right after the barrier: issued before it so that their latency hides behind the wait
@@ -973,7 +979,7 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   const int xs_cap = kpmax + XS_PAD;
   const size_t fixed = static_cast<size_t>(B) * xs_cap * 2 + part_bytes + (GV_WARPS * GV_MAXB + GV_MAXB) * 4 + 2 * GV_MAXSTAGES * 8 + 256;
   const size_t stage = static_cast<size_t>(GV_TILE) * (1024 + WS_PAD) * 2;
-  const size_t budget = 224 * 1024;
+  const size_t budget = 220 * 1024;   // + ~5 KB static shared memory (layer table, control blocks) <= 227 KB
   TB_CHECK(fixed + 2 * stage <= budget, "decode step shared memory budget exceeded");
   int st = static_cast<int>((budget - fixed) / stage);
   if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;
@@ -1006,6 +1012,7 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
     return 1;
   p.kp_qkv = kpks[0]; p.ks_qkv = kpks[1]; p.kp_o = kpks[2]; p.ks_o = kpks[3]; p.kp_gu = kpks[4]; p.ks_gu = kpks[5];
   p.kp_dn = kpks[6]; p.ks_dn = kpks[7]; p.kp_hd = kpks[8]; p.ks_hd = kpks[9];
+  TB_CHECK(a.layers <= MG_MAX_LAYERS, "fused decode step keeps the layer pointer table in shared memory (<= 48 layers)");
   TB_CHECK(a.heads == a.kvh * MG_G && a.qd == a.heads * MG_HD, "fused decode step is specialised for 128-dim heads, 4 q heads per kv head");
   // every CTA must be resident at once (grid barriers): one CTA per SM by shared-memory footprint, grid = #SMs
   auto launch = [&](auto kern) -> int {
