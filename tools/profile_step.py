@@ -50,7 +50,8 @@ for i in range(a.warm + 1):
                          video_timestamps=stamps, heads=[1] * a.batch, do_sample=False, max_new_tokens=a.max_new, pad_token_id=2)
 torch.cuda.synchronize()
 ms, st = model.engine.last_decode_timing()
-print("ids", out.tolist()[0][:16])
+import hashlib
+print("ids", out.tolist()[0][:16], "sha", hashlib.sha1(str(out.tolist()).encode()).hexdigest()[:12])
 if os.environ.get("TRACE_B200_MEGA_TIMING"):
     tl = model.engine.debug_timeline().double() / 1e3   # us
     names = ["qkv", "sync1", "attn", "sync2", "o", "sync3", "gateup", "sync4", "down"]

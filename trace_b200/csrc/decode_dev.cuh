@@ -192,7 +192,8 @@ struct GvItems {
 // shared memory plus `pf_ahead` further stages ahead in L2 (cp.async.bulk.prefetch.L2): while the consumers sit in a
 // barrier the HBM pipe keeps draining the next rows into L2, and the ring refills from L2 when they resume.
 __device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo,
-                                              int vhi, const GvSmem& m, int stages, int& s, uint32_t& ph, int pf_ahead = 0) {
+                                              int vhi, const GvSmem& m, int stages, int& s, uint32_t& ph, int pf_ahead = 0,
+                                              int max_inflight = 0) {
   const int lane = threadIdx.x & 31;
   const int pitch = KS + WS_PAD;
   GvItems it, pf;
@@ -212,6 +213,13 @@ __device__ __forceinline__ void gemv_producer(const __half* __restrict__ W, int 
     const int tr0 = r0 + it.tile * GV_TILE;
     const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
     mbar_wait(&m.empty[s], ph ^ 1);
+    if (max_inflight > 0) {
+      // request throttle: at most `max_inflight` stages of this SM queued in the memory system.  Every byte beyond the
+      // bandwidth-delay product only lengthens the queue that the latency-critical traffic of the step (barrier words,
+      // activation vectors, K/V rows) has to wait in.
+      const int sd = s >= max_inflight ? s - max_inflight : s - max_inflight + stages;
+      mbar_wait(&m.full[sd], s >= max_inflight ? ph : ph ^ 1);
+    }
     if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
     __syncwarp();
     const int row = tr0 + lane;

@@ -170,16 +170,35 @@ __device__ __forceinline__ void mma_item(float (&c)[4], const uint32_t (&w)[32],
     }
   }
 }
+// Partial sums live in shared memory as [tile][warp][16 rows][NBC batch columns] (NBC = batch bucket 1/2/4/8): the
+// m16n8 accumulator fragment of lane (g, t) holds rows g and g+8, columns 2t and 2t+1, of which only n < NBC are kept.
+// (With 8 columns for every batch size the B=1 step spent 53 KB of shared memory on zeros -- one ring stage.)
+template <int NBC>
 __device__ __forceinline__ void flush_tile(float* p, const float (&c)[4], int g, int t, bool add) {
-  if (add) {
-    p[g * 8 + 2 * t] += c[0]; p[g * 8 + 2 * t + 1] += c[1];
-    p[(g + 8) * 8 + 2 * t] += c[2]; p[(g + 8) * 8 + 2 * t + 1] += c[3];
-  } else {
-    p[g * 8 + 2 * t] = c[0]; p[g * 8 + 2 * t + 1] = c[1];
-    p[(g + 8) * 8 + 2 * t] = c[2]; p[(g + 8) * 8 + 2 * t + 1] = c[3];
+  if (NBC == 1) {
+    if (t == 0) {
+      if (add) { p[g] += c[0]; p[g + 8] += c[2]; }
+      else { p[g] = c[0]; p[g + 8] = c[2]; }
+    }
+  } else if (2 * t < NBC) {
+    float* a = p + g * NBC + 2 * t;
+    float* b = p + (g + 8) * NBC + 2 * t;
+    if (add) { a[0] += c[0]; a[1] += c[1]; b[0] += c[2]; b[1] += c[3]; }
+    else { a[0] = c[0]; a[1] = c[1]; b[0] = c[2]; b[1] = c[3]; }
   }
 }
+// sum of the 8 warps' partials for output idx = (tile*16 + row)*NBC + n
+template <int NBC>
+__device__ __forceinline__ float part_out(const float* s_part, int idx) {
+  const int tile = idx / (GV_TILE * NBC), rn = idx % (GV_TILE * NBC);
+  const float* p = s_part + tile * (GV_WARPS * GV_TILE * NBC) + rn;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < GV_WARPS; ++w) v += p[w * (GV_TILE * NBC)];
+  return v;
+}
 
+template <int NBC>
 __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, int k0, int KP, int KS, int r0, int r1, int vlo,
                                               int vhi, const GvSmem& m, int B, int stages) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,22 +214,27 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
   if (k0 == 0) {
     for (int tile = 0; tile < ntile; ++tile) {
       if (tile >= tlo && tile < thi) continue;
-      float* p = m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * 8);
-      p[g * 8 + 2 * t] = 0.f; p[g * 8 + 2 * t + 1] = 0.f; p[(g + 8) * 8 + 2 * t] = 0.f; p[(g + 8) * 8 + 2 * t + 1] = 0.f;
+      const float z[4] = {0.f, 0.f, 0.f, 0.f};
+      flush_tile<NBC>(m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * NBC), z, g, t, false);
     }
   }
+  // `st` lives in local memory (its address is passed to the shared barrier routine): keep the cursor in registers here
+  int rs = st.s;
+  uint32_t rph = st.ph;
+  const uint32_t tm_base = st.tm_base;
+  const int tm_head = st.tm_head;
   const int n_items = (thi - tlo) * nks;
   const int n_tm = min(st.tm_count, n_items);
   const int ts = n_tm / nks;                      // tiles [0, ts) come from TMEM only; tile ts starts in TMEM (maybe with 0 items)
   const int na = ts * nks;                        // items of the TMEM stream
   const __half* xbase = m.xs + g * (KP + XS_PAD) + warp * ksw + t * 8;
-  float* pbase = m.s_part + (static_cast<size_t>(tlo) * GV_WARPS + warp) * (GV_TILE * 8);
+  float* pbase = m.s_part + (static_cast<size_t>(tlo) * GV_WARPS + warp) * (GV_TILE * NBC);
   const bool add = k0 > 0;
   float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t w[32];
   // parked head of the straddled tile -> ring accumulator
   for (int i = na; i < n_tm; ++i) {
-    tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + i) & (TM_SLOTS - 1)) * 32u, w);
+    tmem_ld_32x32(tm_base + static_cast<uint32_t>((tm_head + i) & (TM_SLOTS - 1)) * 32u, w);
     tmem_ld_wait();
     mma_item(cb, w, xbase + (i - na) * KS, xok, nch);
   }
@@ -221,65 +245,53 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
     else if (ia >= na) ring = true;
     else {
       int ok = 0;
-      if (lane == 0) ok = mbar_test(&m.full[st.s], st.ph) ? 1 : 0;
+      if (lane == 0) ok = mbar_test(&m.full[rs], rph) ? 1 : 0;
       ring = __shfl_sync(0xffffffffu, ok, 0) != 0;
     }
     if (ring) {
       const int j = ib % nks;
-      mbar_wait(&m.full[st.s], st.ph);
-      const __half* wa = m.ws + static_cast<size_t>(st.s) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
+      mbar_wait(&m.full[rs], rph);
+      const __half* wa = m.ws + static_cast<size_t>(rs) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
       const __half* wb = wa + 8 * wpitch;
-      const __half* xp = xbase + j * KS;
-#pragma unroll 4
-      for (int ch = 0; ch < nch; ++ch) {
-        const uint4 a = *reinterpret_cast<const uint4*>(wa + ch * 32);
-        const uint4 b = *reinterpret_cast<const uint4*>(wb + ch * 32);
-        const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
-        mma_16816(cb, a.x, b.x, a.y, b.y, xv.x, xv.y);
-        mma_16816(cb, a.z, b.z, a.w, b.w, xv.z, xv.w);
+      // stage -> registers, hand the stage back to the producer (mbarrier.arrive is a release: it is ordered after the
+      // shared-memory reads above), then the MMA chain: the chain is off the ring's refill cycle
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+        if (ch < nch) {
+          a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+          b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+        }
+        w[ch * 8 + 0] = a.x; w[ch * 8 + 1] = a.y; w[ch * 8 + 2] = a.z; w[ch * 8 + 3] = a.w;
+        w[ch * 8 + 4] = b.x; w[ch * 8 + 5] = b.y; w[ch * 8 + 6] = b.z; w[ch * 8 + 7] = b.w;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&m.empty[st.s]);
-      stream_ring_advance(st, stages);
+      if (lane == 0) mbar_arrive(&m.empty[rs]);
+      if (++rs == stages) { rs = 0; rph ^= 1; }
+      mma_item(cb, w, xbase + j * KS, xok, nch);
       if (j == nks - 1) {
-        flush_tile(pbase + static_cast<size_t>(ib / nks) * (GV_WARPS * GV_TILE * 8), cb, g, t, add);
+        flush_tile<NBC>(pbase + static_cast<size_t>(ib / nks) * (GV_WARPS * GV_TILE * NBC), cb, g, t, add);
         cb[0] = cb[1] = cb[2] = cb[3] = 0.f;
       }
       ++ib;
     } else {
       const int j = ia % nks;
-      tmem_ld_32x32(st.tm_base + static_cast<uint32_t>((st.tm_head + ia) & (TM_SLOTS - 1)) * 32u, w);
+      tmem_ld_32x32(tm_base + static_cast<uint32_t>((tm_head + ia) & (TM_SLOTS - 1)) * 32u, w);
       tmem_ld_wait();
       mma_item(ca, w, xbase + j * KS, xok, nch);
       if (j == nks - 1) {
-        flush_tile(pbase + static_cast<size_t>(ia / nks) * (GV_WARPS * GV_TILE * 8), ca, g, t, add);
+        flush_tile<NBC>(pbase + static_cast<size_t>(ia / nks) * (GV_WARPS * GV_TILE * NBC), ca, g, t, add);
         ca[0] = ca[1] = ca[2] = ca[3] = 0.f;
       }
       ++ia;
     }
   }
-  st.tm_head = (st.tm_head + n_tm) & (TM_SLOTS - 1);
+  st.s = rs;
+  st.ph = rph;
+  st.tm_head = (tm_head + n_tm) & (TM_SLOTS - 1);
   st.tm_count -= n_tm;
   st.seq_left -= n_items - n_tm;                  // ring items of a phase are only taken once its parked items are used up
   stream_skip_empty(st, tab);
-}
-
-// epilogues of the GEMV phases (256 consumer threads, after the partials are complete)
-template <int EPI>
-__device__ __forceinline__ void gemv_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo) {
-  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
-  for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-    const float v = gemv_out(m.s_part, idx);
-    const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
-    if (EPI == 2) {
-      const float partner = __shfl_xor_sync(0xffffffffu, v, 8);
-      if ((row & 1) == 0 && n < B && row < r1) __stcg(out + static_cast<size_t>(n) * ldo + (row >> 1), __float2half_rn(silu_f(v) * partner));
-    } else if (n < B && row < r1) {
-      __half* o = out + static_cast<size_t>(n) * ldo + row;
-      if (EPI == 1) __stcg(o, __float2half_rn(v + __half2float(__ldcg(o))));
-      else __stcg(o, __float2half_rn(v));
-    }
-  }
 }
 
 struct MegaLayer {
@@ -310,7 +322,8 @@ struct MegaParams {
   unsigned long long* dbg;            // optional timeline [2 CTAs][layers][10] of %globaltimer stamps
   int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
   int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
-  int max_tiles, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+  int part_bytes, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+  int max_inflight;                   // producer request throttle in stages (0 = the whole ring)
   int tm_relay;                       // park ring stages in TMEM while waiting in grid barriers (0 = off)
   int gate_mode;                      // producer waits for the attention K/V requests before: 1 the O weights, 2 the gate/up weights, 0 never
 };
@@ -707,12 +720,13 @@ __device__ __forceinline__ const __half* phase_weights(const MegaParams& p, cons
 
 // epilogue of a layer phase (256 consumer threads, after the partials are complete): epi 0 store, 1 residual add in
 // place, 2 SwiGLU pairs
+template <int NBC>
 __device__ __forceinline__ void phase_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo, int epi) {
-  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+  const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (GV_TILE * NBC);
   for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-    const float v = gemv_out(m.s_part, idx);
-    const int row = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3), n = idx & 7;
-    const float partner = __shfl_xor_sync(0xffffffffu, v, 8);
+    const float v = part_out<NBC>(m.s_part, idx);
+    const int row = r0 + idx / NBC, n = idx % NBC;
+    const float partner = __shfl_xor_sync(0xffffffffu, v, NBC);     // the next row of the same batch column
     if (epi == 2) {
       if ((row & 1) == 0 && n < B && row < r1) __stcg(out + static_cast<size_t>(n) * ldo + (row >> 1), __float2half_rn(silu_f(v) * partner));
     } else if (n < B && row < r1) {
@@ -735,7 +749,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
     size_t off = 0;
     m.ws = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(p.stages) * GV_TILE * (1024 + WS_PAD) * 2;
     m.xs = reinterpret_cast<__half*>(smem + off); off += static_cast<size_t>(p.B) * p.xs_cap * 2;
-    m.s_part = reinterpret_cast<float*>(smem + off); off += static_cast<size_t>(p.max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
+    m.s_part = reinterpret_cast<float*>(smem + off); off += static_cast<size_t>(p.part_bytes);
     m.s_red = reinterpret_cast<float*>(smem + off); off += (GV_WARPS * GV_MAXB + GV_MAXB) * 4;
     m.full = reinterpret_cast<uint64_t*>(smem + off); off += GV_MAXSTAGES * 8;
     m.empty = reinterpret_cast<uint64_t*>(smem + off);
@@ -790,7 +804,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
       cta_rows(g.N, r0, r1);
       // head: only the rows some batch row decodes from (heads[] was written by the previous step)
       const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
-      if (vlo < vhi) gemv_producer(phase_weights(p, L, type), g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, p.pf_ahead);
+      if (vlo < vhi) gemv_producer(phase_weights(p, L, type), g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, p.pf_ahead, p.max_inflight);
     }
     return;
   }
@@ -844,14 +858,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
         else stage_x_plain(m.xs, xin, g.K, p.B, k0, g.KP);
         cons_sync();
         if (k0 == 0) { stamp(p, l, 10 + type * 2); stamp_val(p, l, 25 + type, static_cast<unsigned long long>(st.tm_count)); }
-        consume_phase(st, s_tab, k0, g.KP, g.KS, r0, r1, vlo, vhi, m, p.B, p.stages);
+        consume_phase<NB>(st, s_tab, k0, g.KP, g.KS, r0, r1, vlo, vhi, m, p.B, p.stages);
       }
       cons_sync();
       stamp(p, l, 11 + type * 2);
     }
     if (type < 4) {
       __half* out = type == 0 ? p.qkv : type == 2 ? p.act : p.x;
-      phase_epilogue(m, r0, r1, p.B, out, type == 0 ? p.qkvw : type == 2 ? p.ffn : p.H, type == 2 ? 2 : (type == 0 ? 0 : 1));
+      phase_epilogue<NB>(m, r0, r1, p.B, out, type == 0 ? p.qkvw : type == 2 ? p.ffn : p.H, type == 2 ? 2 : (type == 0 ? 0 : 1));
       stamp(p, l, type * 2 + (type > 0 ? 3 : 1));
       if (type == 0) {
         grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);               // q, k, v complete
@@ -862,17 +876,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
       }
     } else {
       // ---- heads: logits of the active ranges (fp16-rounded like the reference's fp16 GEMM) + argmax candidates ----
-      const int n = threadIdx.x & 7;
+      const int n = threadIdx.x % NB;          // 256 % NB == 0: the batch column of a thread is fixed
       float bv = -INFINITY;
       int bi = 0x7fffffff;
-      const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * 128;
+      const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (GV_TILE * NB);
       __shared__ float s_cv[GV_WARPS][8];
       __shared__ int s_ci[GV_WARPS][8];
       if (vlo < vhi) {
         const int lo = s_hlo[n], hi = s_hhi[n];
         for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-          const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
-          float v = __half2float(__float2half_rn(gemv_out(m.s_part, idx)));
+          const int r = r0 + idx / NB;
+          float v = __half2float(__float2half_rn(part_out<NB>(m.s_part, idx)));
           const bool act = (n < p.B) && r < r1 && r >= lo && r < hi;
           if (!act) v = -INFINITY;
           if (p.logits_out != nullptr && n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = v;
@@ -880,17 +894,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
         }
       } else if (p.logits_out != nullptr) {
         for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-          const int r = r0 + (idx >> 7) * GV_TILE + ((idx & 127) >> 3);
+          const int r = r0 + idx / NB;
           if (n < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(n) * p.n_valid + r] = -INFINITY;
         }
       }
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
+      for (int o = NB; o <= 16; o <<= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      if ((threadIdx.x & 31) < 8) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
+      if ((threadIdx.x & 31) < NB) { s_cv[threadIdx.x >> 5][n] = bv; s_ci[threadIdx.x >> 5][n] = bi; }
       cons_sync();
       if (threadIdx.x < p.B) {
         float v = s_cv[0][threadIdx.x];
@@ -974,8 +988,10 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   const int chunk_max = (((max_ctx + nsplit - 1) / nsplit) + 31) & ~31;
   // attention scratch lives in the s_part region: qs + knew + vnew + red + sc
   const size_t attn_scratch = (static_cast<size_t>(MG_G) * MG_HD + 2 * MG_HD + GV_WARPS * MG_G * MG_HD + GV_WARPS * MG_G * 2) * 4;
-  size_t part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4;
-  while (part_bytes < attn_scratch) { ++max_tiles; part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * 8 * 4; }
+  const int nbc = B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8;     // batch bucket = kernel template argument
+  size_t part_bytes = static_cast<size_t>(max_tiles) * GV_WARPS * GV_TILE * nbc * 4;
+  if (part_bytes < attn_scratch) part_bytes = attn_scratch;
+  part_bytes = (part_bytes + 127) & ~static_cast<size_t>(127);
   const int xs_cap = kpmax + XS_PAD;
   const size_t fixed = static_cast<size_t>(B) * xs_cap * 2 + part_bytes + (GV_WARPS * GV_MAXB + GV_MAXB) * 4 + 2 * GV_MAXSTAGES * 8 + 256;
   const size_t stage = static_cast<size_t>(GV_TILE) * (1024 + WS_PAD) * 2;
@@ -985,7 +1001,7 @@ int decode_mega_plan(int B, int H, int qkvw, int qd, int ffn, int head_rows, int
   if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;
   *nsplit_out = nsplit;
   *chunk_max_out = chunk_max;
-  *max_tiles_out = max_tiles;
+  *max_tiles_out = static_cast<int>(part_bytes);
   *stages_out = st;
   *xs_cap_out = xs_cap;
   *smem_out = fixed + st * stage;
@@ -1004,10 +1020,11 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
   p.pf_ahead = a.pf_ahead; p.pf_gap_kb = a.pf_gap_kb; p.pf_attn_kb = a.pf_attn_kb;
   p.tm_relay = a.tm_relay; p.gate_mode = a.gate_mode;
+  p.max_inflight = a.max_inflight;
   p.dbg = a.dbg;
   int kpks[10];
   size_t smem = 0;
-  if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.max_tiles,
+  if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.part_bytes,
                        &p.stages, &p.xs_cap, &smem))
     return 1;
   p.kp_qkv = kpks[0]; p.ks_qkv = kpks[1]; p.kp_o = kpks[2]; p.ks_o = kpks[3]; p.kp_gu = kpks[4]; p.ks_gu = kpks[5];
