@@ -723,10 +723,14 @@ __device__ __forceinline__ const __half* phase_weights(const MegaParams& p, cons
 template <int NBC>
 __device__ __forceinline__ void phase_epilogue(const GvSmem& m, int r0, int r1, int B, __half* out, int ldo, int epi) {
   const int nout = ((r1 - r0 + GV_TILE - 1) / GV_TILE) * (GV_TILE * NBC);
-  for (int idx = threadIdx.x; idx < nout; idx += GV_CONS) {
-    const float v = part_out<NBC>(m.s_part, idx);
+  // warp-uniform trip count (nout is only a multiple of 16*NBC): the SwiGLU partner exchange is a full-warp shuffle
+  for (int base = 0; base < nout; base += GV_CONS) {
+    const int idx = base + threadIdx.x;
+    const bool in = idx < nout;
+    const float v = in ? part_out<NBC>(m.s_part, idx) : 0.f;
     const int row = r0 + idx / NBC, n = idx % NBC;
     const float partner = __shfl_xor_sync(0xffffffffu, v, NBC);     // the next row of the same batch column
+    if (!in) continue;
     if (epi == 2) {
       if ((row & 1) == 0 && n < B && row < r1) __stcg(out + static_cast<size_t>(n) * ldo + (row >> 1), __float2half_rn(silu_f(v) * partner));
     } else if (n < B && row < r1) {
