@@ -740,7 +740,10 @@ __device__ __forceinline__ void phase_epilogue(const GvSmem& m, int r0, int r1, 
   }
 }
 
-__device__ __noinline__ void grid_sync_shared(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, const GvSmem& m, int stages) {
+// One copy of the barrier + relay code for all call sites.  `m` is passed BY VALUE: taking its address would force the
+// kernel's copy into local memory and every shared-memory access derived from it (the whole consume loop) would be
+// compiled as a generic LD/ST instead of LDS/STS.
+__device__ __noinline__ void grid_sync_shared(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, GvSmem m, int stages) {
   grid_sync(bar, target, st, tab, m, stages);
 }
 
