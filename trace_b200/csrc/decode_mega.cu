@@ -200,7 +200,7 @@ __device__ __forceinline__ float part_out(const float* s_part, int idx) {
 
 template <int NBC>
 __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, int k0, int KP, int KS, int r0, int r1, int vlo,
-                                              int vhi, const GvSmem& m, int B, int stages) {
+                                              int vhi, const GvSmem& m, int B, int stages, int early_release) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
@@ -265,10 +265,16 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
         w[ch * 8 + 0] = a.x; w[ch * 8 + 1] = a.y; w[ch * 8 + 2] = a.z; w[ch * 8 + 3] = a.w;
         w[ch * 8 + 4] = b.x; w[ch * 8 + 5] = b.y; w[ch * 8 + 6] = b.z; w[ch * 8 + 7] = b.w;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&m.empty[rs]);
+      if (early_release) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&m.empty[rs]);
+        mma_item(cb, w, xbase + j * KS, xok, nch);
+      } else {
+        mma_item(cb, w, xbase + j * KS, xok, nch);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&m.empty[rs]);
+      }
       if (++rs == stages) { rs = 0; rph ^= 1; }
-      mma_item(cb, w, xbase + j * KS, xok, nch);
       if (j == nks - 1) {
         flush_tile<NBC>(pbase + static_cast<size_t>(ib / nks) * (GV_WARPS * GV_TILE * NBC), cb, g, t, add);
         cb[0] = cb[1] = cb[2] = cb[3] = 0.f;
@@ -323,6 +329,7 @@ struct MegaParams {
   int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
   int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
   int part_bytes, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+  int early_release;                  // hand a ring stage back before (1) or after (0) its MMA chain
   int max_inflight;                   // producer request throttle in stages (0 = the whole ring)
   int tm_relay;                       // park ring stages in TMEM while waiting in grid barriers (0 = off)
   int gate_mode;                      // producer waits for the attention K/V requests before: 1 the O weights, 2 the gate/up weights, 0 never
@@ -865,7 +872,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
         else stage_x_plain(m.xs, xin, g.K, p.B, k0, g.KP);
         cons_sync();
         if (k0 == 0) { stamp(p, l, 10 + type * 2); stamp_val(p, l, 25 + type, static_cast<unsigned long long>(st.tm_count)); }
-        consume_phase<NB>(st, s_tab, k0, g.KP, g.KS, r0, r1, vlo, vhi, m, p.B, p.stages);
+        consume_phase<NB>(st, s_tab, k0, g.KP, g.KS, r0, r1, vlo, vhi, m, p.B, p.stages, p.early_release);
       }
       cons_sync();
       stamp(p, l, 11 + type * 2);
@@ -1027,13 +1034,14 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
   p.pf_ahead = a.pf_ahead; p.pf_gap_kb = a.pf_gap_kb; p.pf_attn_kb = a.pf_attn_kb;
   p.tm_relay = a.tm_relay; p.gate_mode = a.gate_mode;
-  p.max_inflight = a.max_inflight;
+  p.max_inflight = a.max_inflight; p.early_release = a.early_release;
   p.dbg = a.dbg;
   int kpks[10];
   size_t smem = 0;
   if (decode_mega_plan(a.B, a.H, a.qkvw, a.qd, a.ffn, a.head_rows, a.max_ctx, a.kvh, a.num_sms, &p.nsplit, &p.chunk_max, kpks, &p.part_bytes,
                        &p.stages, &p.xs_cap, &smem))
     return 1;
+  if (a.max_stages > 1 && p.stages > a.max_stages) { smem -= static_cast<size_t>(p.stages - a.max_stages) * GV_TILE * (1024 + WS_PAD) * 2; p.stages = a.max_stages; }
   p.kp_qkv = kpks[0]; p.ks_qkv = kpks[1]; p.kp_o = kpks[2]; p.ks_o = kpks[3]; p.kp_gu = kpks[4]; p.ks_gu = kpks[5];
   p.kp_dn = kpks[6]; p.ks_dn = kpks[7]; p.kp_hd = kpks[8]; p.ks_hd = kpks[9];
   TB_CHECK(a.layers <= MG_MAX_LAYERS, "fused decode step keeps the layer pointer table in shared memory (<= 48 layers)");
