@@ -160,14 +160,29 @@ __device__ __forceinline__ void barrier_poller(const unsigned* bar, StreamTab& t
 // The parked head of the straddled tile is folded into the ring accumulator first.  A tile is always accumulated in
 // k order in one accumulator, so the result does not depend on how many stages were parked or on the interleaving.
 // Warps run decoupled inside a phase (each owns a K slice of every stage) and meet again at the caller's cons_sync.
+template <bool FULL>
 __device__ __forceinline__ void mma_item(float (&c)[4], const uint32_t (&w)[32], const __half* xp, bool xok, int nch) {
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
-    if (ch < nch) {
+    if (FULL || ch < nch) {
       const uint4 xv = xok ? *reinterpret_cast<const uint4*>(xp + ch * 32) : make_uint4(0, 0, 0, 0);
       mma_16816(c, w[ch * 8 + 0], w[ch * 8 + 4], w[ch * 8 + 1], w[ch * 8 + 5], xv.x, xv.y);
       mma_16816(c, w[ch * 8 + 2], w[ch * 8 + 6], w[ch * 8 + 3], w[ch * 8 + 7], xv.z, xv.w);
     }
+  }
+}
+// the warp's K slice of one ring stage -> registers (FULL: KS = 1024, 4 chunks of 32 columns, no predicates)
+template <bool FULL>
+__device__ __forceinline__ void load_item(uint32_t (&w)[32], const __half* wa, const __half* wb, int nch) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (FULL || ch < nch) {
+      a = *reinterpret_cast<const uint4*>(wa + ch * 32);
+      b = *reinterpret_cast<const uint4*>(wb + ch * 32);
+    }
+    w[ch * 8 + 0] = a.x; w[ch * 8 + 1] = a.y; w[ch * 8 + 2] = a.z; w[ch * 8 + 3] = a.w;
+    w[ch * 8 + 4] = b.x; w[ch * 8 + 5] = b.y; w[ch * 8 + 6] = b.z; w[ch * 8 + 7] = b.w;
   }
 }
 // Partial sums live in shared memory as [tile][warp][16 rows][NBC batch columns] (NBC = batch bucket 1/2/4/8): the
@@ -233,12 +248,16 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
   float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t w[32];
   // parked head of the straddled tile -> ring accumulator
+  const bool full = nch == 4;
   for (int i = na; i < n_tm; ++i) {
     tmem_ld_32x32(tm_base + static_cast<uint32_t>((tm_head + i) & (TM_SLOTS - 1)) * 32u, w);
     tmem_ld_wait();
-    mma_item(cb, w, xbase + (i - na) * KS, xok, nch);
+    mma_item<false>(cb, w, xbase + (i - na) * KS, xok, nch);
   }
   int ia = 0, ib = n_tm;
+  int ja = 0, jb = n_tm - na;                     // k-stage index inside the current tile of each stream
+  float* pa = pbase;                              // partial-sum block of the current tile of each stream
+  float* pb = pbase + static_cast<size_t>(ts) * (GV_WARPS * GV_TILE * NBC);
   while (ia < na || ib < n_items) {
     bool ring;
     if (ib >= n_items) ring = false;
@@ -249,45 +268,41 @@ __device__ __forceinline__ void consume_phase(Stream& st, const StreamTab& tab, 
       ring = __shfl_sync(0xffffffffu, ok, 0) != 0;
     }
     if (ring) {
-      const int j = ib % nks;
       mbar_wait(&m.full[rs], rph);
       const __half* wa = m.ws + static_cast<size_t>(rs) * m.ws_stride + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
       const __half* wb = wa + 8 * wpitch;
+      const __half* xp = xbase + jb * KS;
       // stage -> registers, hand the stage back to the producer (mbarrier.arrive is a release: it is ordered after the
       // shared-memory reads above), then the MMA chain: the chain is off the ring's refill cycle
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-        if (ch < nch) {
-          a = *reinterpret_cast<const uint4*>(wa + ch * 32);
-          b = *reinterpret_cast<const uint4*>(wb + ch * 32);
-        }
-        w[ch * 8 + 0] = a.x; w[ch * 8 + 1] = a.y; w[ch * 8 + 2] = a.z; w[ch * 8 + 3] = a.w;
-        w[ch * 8 + 4] = b.x; w[ch * 8 + 5] = b.y; w[ch * 8 + 6] = b.z; w[ch * 8 + 7] = b.w;
-      }
+      if (full) load_item<true>(w, wa, wb, nch);
+      else load_item<false>(w, wa, wb, nch);
       if (early_release) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&m.empty[rs]);
-        mma_item(cb, w, xbase + j * KS, xok, nch);
-      } else {
-        mma_item(cb, w, xbase + j * KS, xok, nch);
+      }
+      if (full) mma_item<true>(cb, w, xp, xok, nch);
+      else mma_item<false>(cb, w, xp, xok, nch);
+      if (!early_release) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&m.empty[rs]);
       }
       if (++rs == stages) { rs = 0; rph ^= 1; }
-      if (j == nks - 1) {
-        flush_tile<NBC>(pbase + static_cast<size_t>(ib / nks) * (GV_WARPS * GV_TILE * NBC), cb, g, t, add);
+      if (++jb == nks) {
+        flush_tile<NBC>(pb, cb, g, t, add);
         cb[0] = cb[1] = cb[2] = cb[3] = 0.f;
+        jb = 0;
+        pb += GV_WARPS * GV_TILE * NBC;
       }
       ++ib;
     } else {
-      const int j = ia % nks;
       tmem_ld_32x32(tm_base + static_cast<uint32_t>((tm_head + ia) & (TM_SLOTS - 1)) * 32u, w);
       tmem_ld_wait();
-      mma_item(ca, w, xbase + j * KS, xok, nch);
-      if (j == nks - 1) {
-        flush_tile<NBC>(pbase + static_cast<size_t>(ia / nks) * (GV_WARPS * GV_TILE * NBC), ca, g, t, add);
+      mma_item<false>(ca, w, xbase + ja * KS, xok, nch);
+      if (++ja == nks) {
+        flush_tile<NBC>(pa, ca, g, t, add);
         ca[0] = ca[1] = ca[2] = ca[3] = 0.f;
+        ja = 0;
+        pa += GV_WARPS * GV_TILE * NBC;
       }
       ++ia;
     }
