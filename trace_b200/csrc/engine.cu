@@ -91,7 +91,7 @@ struct trace_b200_ctx {
   unsigned* d_gbar = nullptr;
   unsigned long long* d_dbg = nullptr;
   bool fused_decode = true;
-  int tm_relay = 1, gate_mode = 2, pf_ahead = 0, pf_gap_kb = 0, pf_attn_kb = 0, max_inflight = 0, early_release = 1, max_stages = 0;   // fused decode-step switches (kernels.h)
+  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, pf_gap_kb = 0, pf_attn_kb = 0, max_inflight = 0, early_release = 1, max_stages = 4;   // fused decode-step switches (kernels.h)
   bool attn_tc = false;           // tcgen05 attention (attention_tc.cu) instead of the mma.sync kernel
 };
 
@@ -235,14 +235,17 @@ int allocate_all(trace_b200_ctx* ctx) {
       const char* e = getenv(name);
       return (e != nullptr && atoi(e) >= lo && atoi(e) <= hi) ? atoi(e) : dflt;
     };
-    ctx->tm_relay = env_int("TRACE_B200_TM_RELAY", 0, 2, 1);
+    // measured on B200 (profiles/r01_decode_ab.md): the TMEM reservoir keeps HBM busy through the grid barriers, but the
+    // barrier words then queue behind the weight stream and every barrier gets 2-4 us longer -- net loss, so it is off
+    // by default; a ring of 4 stages is as fast as 3 and faster than 5 (the queue only adds latency once HBM is saturated)
+    ctx->tm_relay = env_int("TRACE_B200_TM_RELAY", 0, 2, 0);
     ctx->gate_mode = env_int("TRACE_B200_GATE_MODE", 0, 2, ctx->tm_relay ? 2 : 1);
     ctx->pf_ahead = env_int("TRACE_B200_PF_AHEAD", 0, 64, 0);
     ctx->pf_gap_kb = env_int("TRACE_B200_PF_GAP_KB", 0, 4096, 0);
     ctx->pf_attn_kb = env_int("TRACE_B200_PF_ATTN_KB", 0, 4096, 0);
     ctx->max_inflight = env_int("TRACE_B200_INFLIGHT", 0, 3, 0);
     ctx->early_release = env_int("TRACE_B200_EARLY_REL", 0, 1, 1);
-    ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
+    ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 4);
     const char* env2 = getenv("TRACE_B200_ATTN_TC");
     ctx->attn_tc = (env2 != nullptr) ? atoi(env2) == 1 : false;
   }
