@@ -70,7 +70,9 @@ int trace_b200_encode_frames(trace_b200_ctx* ctx, const void* pixels, int F, voi
 /* prepare_inputs_labels_for_multimodal, prefill branch (trace_arch.py:377-426) + the time rows of
  * encode_images_or_videos (trace_arch.py:237-258).  ids [B,L] int64 with exactly one -201 per row and -205
  * for <sync>; slots [B*T*8, hidden]; time_ids [B,T,6] int32 (host-formatted '0>6.1f' ids, time_encoder.py:58).
- * embeds_out [B, L-1+14T, hidden] fp16. */
+ * embeds_out [B, L-1+14T, hidden] fp16.
+ * T == 0 (slots and time_ids may be NULL) is the text-only branch of generate (trace_mistral.py:306-307,
+ * `embed_tokens(inputs)`): embeds_out [B, L, hidden]. */
 int trace_b200_build_prefill(trace_b200_ctx* ctx, const int64_t* ids_dev, int B, int L, int T, const void* slots,
                              const int32_t* time_ids_dev, void* embeds_out, void* stream);
 

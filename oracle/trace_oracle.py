@@ -238,8 +238,12 @@ class TraceOracle:
         head) when return_trace].  `head` None reproduces trace/__init__.py:infer (text head only)."""
         d = self.d
         swap = {d.vocab: 1, d.time_base: 2, d.score_base: 0}                          # trace_mistral.py:86-88
-        vis = self.encode_clip(pixels, video_timestamps)
-        e = self.splice(ids, vis)
+        if pixels is None:                                                            # trace_mistral.py:306-307: plain text generate
+            vis = None
+            e = torch.stack([self.embed_token(int(i)) for i in ids], 0)
+        else:
+            vis = self.encode_clip(pixels, video_timestamps)
+            e = self.splice(ids, vis)
         h, cache = self.llm_forward(e, None)
         out: List[int] = []
         trace = []

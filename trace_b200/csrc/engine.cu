@@ -584,7 +584,8 @@ int trace_b200_encode_frames(trace_b200_ctx* ctx, const void* pixels, int F, voi
 int trace_b200_build_prefill(trace_b200_ctx* ctx, const int64_t* ids_dev, int B, int L, int T, const void* slots,
                              const int32_t* time_ids_dev, void* embeds_out, void* stream) {
   TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
-  TB_CHECK(ids_dev && slots && time_ids_dev && embeds_out && B > 0 && L > 0 && T > 0, "bad arguments");
+  TB_CHECK(ids_dev && embeds_out && B > 0 && L > 0 && T >= 0, "bad arguments");
+  TB_CHECK(T == 0 || (slots != nullptr && time_ids_dev != nullptr), "slots / time ids missing");
   TB_CUDA(cudaSetDevice(ctx->device));
   RUN(splice_prefill(ids_dev, B, L, T, static_cast<const __half*>(slots), time_ids_dev, ctx->embed, ctx->time_tab, ctx->sync_tab,
                      ctx->c.vocab, ctx->c.hidden, static_cast<__half*>(embeds_out), static_cast<cudaStream_t>(stream)));

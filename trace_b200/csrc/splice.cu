@@ -21,7 +21,7 @@ splice_kernel(const int64_t* __restrict__ ids, int L, int T, int vpos_hint, cons
     int v = -1;
     for (int i = 0; i < L; ++i)
       if (row_ids[i] == -201 || row_ids[i] == -200) { v = i; break; }
-    s_vpos = v;
+    s_vpos = v < 0 ? 0x7fffffff : v;   // no placeholder (text-only prompt, T == 0): every row is a plain gather
   }
   __syncthreads();
   const int vpos = s_vpos;
@@ -50,7 +50,7 @@ int splice_prefill(const int64_t* ids, int B, int L, int T, const __half* slots,
                    __half* out, cudaStream_t stream) {
   (void)vocab;
   TB_CHECK(H % 8 == 0, "hidden size must be a multiple of 8");
-  const int S = L - 1 + 14 * T;
+  const int S = T == 0 ? L : L - 1 + 14 * T;   // T == 0: text-only prompt, embed_tokens(inputs) (trace_mistral.py:306-307)
   if (B == 0) return 0;
   splice_kernel<<<dim3(S, B), 128, 0, stream>>>(ids, L, T, 0, slots, time_ids, embed, time_tab, sync_tab, H, out, S);
   TB_LAUNCH_OK();

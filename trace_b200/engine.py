@@ -160,11 +160,16 @@ class Engine:
         _check(self.lib.trace_b200_encode_frames(self._h, px.data_ptr(), F, slots.data_ptr(), _ptr(feats), _stream()))
         return (slots, feats) if return_feats else slots
 
-    def build_prefill(self, ids: torch.Tensor, slots: torch.Tensor, time_ids: torch.Tensor) -> torch.Tensor:
-        """ids [B,L] int64 (one -201 per row), slots [B,T,8,H] fp16, time_ids [B,T,6] int32 -> embeds [B,S,H]."""
+    def build_prefill(self, ids: torch.Tensor, slots: Optional[torch.Tensor], time_ids: Optional[torch.Tensor]) -> torch.Tensor:
+        """ids [B,L] int64 (one -201 per row), slots [B,T,8,H] fp16, time_ids [B,T,6] int32 -> embeds [B,S,H].
+        slots=None / time_ids=None: text-only prompt, plain `embed_tokens(ids)` -> [B,L,H]."""
         assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous()
-        assert time_ids.is_cuda and time_ids.dtype == torch.int32 and time_ids.is_contiguous()
         B, L = ids.shape
+        if slots is None:
+            out = torch.empty((B, L, self.dims.hidden), dtype=torch.float16, device=ids.device)
+            _check(self.lib.trace_b200_build_prefill(self._h, ids.data_ptr(), B, L, 0, None, None, out.data_ptr(), _stream()))
+            return out
+        assert time_ids.is_cuda and time_ids.dtype == torch.int32 and time_ids.is_contiguous()
         T = time_ids.shape[1]
         S = L - 1 + self.dims.tokens_per_frame * T
         sl = _f16c(slots)

@@ -143,56 +143,25 @@ class TraceMistralForCausalLM:
             slots = self.engine.encode_frames(frames)
         return slots.view(B, T, synth.NUM_SLOTS, self.dims.hidden)
 
-    @torch.no_grad()
-    def generate(self, inputs: Optional[torch.Tensor] = None, images_or_videos=None, times=None, scores=None,
-                 video_timestamps=None, modal_list=None, **kwargs):
-        if "inputs_embeds" in kwargs:
-            raise NotImplementedError("`inputs_embeds` is not supported")                       # trace_mistral.py:282-283
-        attention_mask = kwargs.pop("attention_mask", None)
-        kwargs.pop("position_ids", None)
-        heads = kwargs.pop("heads", None)
-        max_new = kwargs.pop("max_new_tokens", None) or 20
-        do_sample = kwargs.pop("do_sample", False)
-        kwargs.pop("temperature", None)
-        kwargs.pop("use_cache", None)
-        kwargs.pop("stopping_criteria", None)   # constructed by every driver, only trace/__init__.py passes it
-        pad = kwargs.pop("pad_token_id", None)
-        eos = kwargs.pop("eos_token_id", None) or self.generation_config.eos_token_id
-        if pad is None:
-            pad = eos
-        if do_sample:
-            raise NotImplementedError("trace_b200 implements the greedy path of the BASELINE configs (do_sample=False)")
-        if images_or_videos is None:
-            raise NotImplementedError("text-only generate (images_or_videos=None) is not on the accelerated path")
-        assert inputs is not None and inputs.dim() == 2
-        B, L = inputs.shape
-        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
-            raise NotImplementedError("left/right padded prompts are not supported (the reference cannot batch them either, SURVEY §9-14)")
-        if heads is not None:
-            assert len(heads) == B                                                               # trace_mistral.py:245
-        modal_list = modal_list or ["video"] * B
-        nf = self.num_frames()
-        clips = [x.unsqueeze(0).expand(nf, -1, -1, -1) if m == "image" else x for x, m in zip(images_or_videos, modal_list)]
-        T = clips[0].shape[0]
-        if any(c.shape != clips[0].shape for c in clips):
-            raise RuntimeError("stack expects each tensor to be equal size (clips of one batch must share T)")  # trace_arch.py:222
-        ids = inputs.to(self.device, torch.int64).contiguous()
-        nvid = ((ids == MMODAL_TOKEN_INDEX["VIDEO"]) | (ids == MMODAL_TOKEN_INDEX["IMAGE"])).sum(1)
-        assert bool((nvid == 1).all()), "only have one video inputs!"                            # trace_arch.py:408
-        if video_timestamps is None:
-            raise NotImplementedError("video_timestamps=None (no time rows) is not used by any TRACE driver")
-        tid = torch.tensor([frame_time_ids(ts) for ts in video_timestamps], dtype=torch.int32, device=self.device)
-        assert tid.shape == (B, T, 6), f"time ids shape {tuple(tid.shape)}"
-        slots = self._encode_slots(clips)
+    def _generate_from_slots(self, ids: torch.Tensor, slots: torch.Tensor, tid: torch.Tensor, heads, max_new: int, eos: int,
+                             pad: int) -> torch.Tensor:
+        """Splice + prefill + greedy decode for rows whose visual tokens are already encoded.
+        ids [B,L] int64, slots [B,T,8,H] fp16, tid [B,T,6] int32 (all on the engine's device); `heads` (list or None)
+        is mutated in place.  Rows are decoded in groups of <= 8 (TRACE_B200_MAX_DECODE_BATCH)."""
+        B, L = ids.shape
+        T = 0 if tid is None else tid.shape[1]
         out_rows: List[torch.Tensor] = []
         hd_all = [(-1 if heads is None else int(h)) for h in (heads if heads is not None else [0] * B)]
-        S = L - 1 + self.dims.tokens_per_frame * T
+        S = L if slots is None else L - 1 + self.dims.tokens_per_frame * T
         if S + max_new > self.engine.max_ctx:
             raise TraceB200Error(f"prompt ({S}) + max_new_tokens ({max_new}) exceeds the engine context ({self.engine.max_ctx})")
         n_final = 0
         for b0 in range(0, B, 8):
             b1 = min(B, b0 + 8)
-            embeds = self.engine.build_prefill(ids[b0:b1].contiguous(), slots[b0:b1].contiguous(), tid[b0:b1].contiguous())
+            if slots is None:
+                embeds = self.engine.build_prefill(ids[b0:b1].contiguous(), None, None)
+            else:
+                embeds = self.engine.build_prefill(ids[b0:b1].contiguous(), slots[b0:b1].contiguous(), tid[b0:b1].contiguous())
             kv = [self.engine.alloc_slot(S + max_new) for _ in range(b1 - b0)]
             try:
                 self.engine.prefill(kv, embeds)
@@ -212,4 +181,50 @@ class TraceMistralForCausalLM:
         for out in out_rows:
             res[r: r + out.shape[0], : out.shape[1]] = out
             r += out.shape[0]
+        return res
+
+    @torch.no_grad()
+    def generate(self, inputs: Optional[torch.Tensor] = None, images_or_videos=None, times=None, scores=None,
+                 video_timestamps=None, modal_list=None, **kwargs):
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported")                       # trace_mistral.py:282-283
+        attention_mask = kwargs.pop("attention_mask", None)
+        kwargs.pop("position_ids", None)
+        heads = kwargs.pop("heads", None)
+        max_new = kwargs.pop("max_new_tokens", None) or 20
+        do_sample = kwargs.pop("do_sample", False)
+        kwargs.pop("temperature", None)
+        kwargs.pop("use_cache", None)
+        kwargs.pop("stopping_criteria", None)   # constructed by every driver, only trace/__init__.py passes it
+        pad = kwargs.pop("pad_token_id", None)
+        eos = kwargs.pop("eos_token_id", None) or self.generation_config.eos_token_id
+        if pad is None:
+            pad = eos
+        if do_sample:
+            raise NotImplementedError("trace_b200 implements the greedy path of the BASELINE configs (do_sample=False)")
+        assert inputs is not None and inputs.dim() == 2
+        B, L = inputs.shape
+        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
+            raise NotImplementedError("left/right padded prompts are not supported (the reference cannot batch them either, SURVEY §9-14)")
+        if heads is not None:
+            assert len(heads) == B                                                               # trace_mistral.py:245
+        if images_or_videos is None:
+            # plain text generate: inputs_embeds = embed_tokens(inputs) (trace_mistral.py:306-307)
+            ids = inputs.to(self.device, torch.int64).contiguous()
+            return self._generate_from_slots(ids, None, None, heads, max_new, eos, pad).to(inputs.device)
+        modal_list = modal_list or ["video"] * B
+        nf = self.num_frames()
+        clips = [x.unsqueeze(0).expand(nf, -1, -1, -1) if m == "image" else x for x, m in zip(images_or_videos, modal_list)]
+        T = clips[0].shape[0]
+        if any(c.shape != clips[0].shape for c in clips):
+            raise RuntimeError("stack expects each tensor to be equal size (clips of one batch must share T)")  # trace_arch.py:222
+        ids = inputs.to(self.device, torch.int64).contiguous()
+        nvid = ((ids == MMODAL_TOKEN_INDEX["VIDEO"]) | (ids == MMODAL_TOKEN_INDEX["IMAGE"])).sum(1)
+        assert bool((nvid == 1).all()), "only have one video inputs!"                            # trace_arch.py:408
+        if video_timestamps is None:
+            raise NotImplementedError("video_timestamps=None (no time rows) is not used by any TRACE driver")
+        tid = torch.tensor([frame_time_ids(ts) for ts in video_timestamps], dtype=torch.int32, device=self.device)
+        assert tid.shape == (B, T, 6), f"time ids shape {tuple(tid.shape)}"
+        slots = self._encode_slots(clips)
+        res = self._generate_from_slots(ids, slots, tid, heads, max_new, eos, pad)
         return res.to(inputs.device)
