@@ -37,6 +37,9 @@ import torch  # noqa: E402
 TOKENS_PER_EVENT = 40     # synth.TOKENS_PER_EVENT: 13 time + 4 score + 22 caption + 1 <sync>
 L_TEXT = 224              # fixed prompt length
 MAX_NEW = 512             # evaluate.py:449
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_step_kernel launch (ncu, B=1, context ~2020), see profiles/
+NCU_DRAM_BYTES_PER_LAUNCH = 14244.01e6 + 145.32e6
+NCU_DRAM_SOURCE = "profiles/r01_launches_final.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, per launch)"
 
 
 def parse_args():
@@ -343,7 +346,33 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    # ---- per-stage device times outside the timed regions (explain the headline; not part of `value`) ----
+    def timed(fn, reps=3):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    from trace_b200.model.encoders import frame_time_ids
+    ms_vit = timed(lambda: eng.encode_frames(clips_dev[0]))
+    slots0 = eng.encode_frames(clips_dev[0]).view(1, T, 8, d.hidden)
+    tid0 = torch.tensor([frame_time_ids(stamps[0])], dtype=torch.int32, device="cuda")
+
+    def prefill_once():
+        emb = eng.build_prefill(ids, slots0, tid0)
+        kv = [eng.alloc_slot(S + 8)]
+        eng.prefill(kv, emb)
+        eng.free_slot(kv[0])
+
+    ms_prefill = timed(prefill_once)
     hbm_peak, tf_peak, peak_src = peaks()
+    vit_flop = 366.0e9 * T                                          # 23 of 24 blocks + patch embed
+    prefill_flop = 2 * 6.979e9 * S + 262144.0 * S * S
     # algorithmic bytes of one decode step at B=1: fp16 layer weights + head actually read + KV
     layer_w = d.layers * ((d.heads + 2 * d.kv_heads) * d.head_dim * d.hidden + d.heads * d.head_dim * d.hidden + 3 * d.ffn * d.hidden) * 2
     text_frac = 23.0 / TOKENS_PER_EVENT if args.weights == "structured" else 1.0
@@ -373,8 +402,15 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps},
         "roofline": {"bound": "hbm", "kernel": "decode_step_kernel (one launch per generated token: 32 layers + heads + argmax/head-switch)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
-                     "traffic": None, "bytes_per_step": bytes_step, "ms_per_decode_step": step_ms,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE, "bytes_per_step": bytes_step, "ms_per_decode_step": step_ms,
                      "decode_share_of_step": dec_ms / ms_total},
+        "stages": {
+            "vit_encode": {"ms": ms_vit, "tflops": vit_flop / (ms_vit * 1e-3) / 1e12, "frac_of_tensor_peak": vit_flop / (ms_vit * 1e-3) / 1e12 / tf_peak,
+                           "tensor_peak_tflops": tf_peak, "flop": vit_flop, "note": "CLIP-ViT-L/14-336 x%d frames + slot pool, tcgen05 GEMMs; tensor-pipe %% per kernel from ncu in profiles/" % T},
+            "prefill": {"ms": ms_prefill, "tflops": prefill_flop / (ms_prefill * 1e-3) / 1e12,
+                        "frac_of_tensor_peak": prefill_flop / (ms_prefill * 1e-3) / 1e12 / tf_peak, "flop": prefill_flop, "tokens": S},
+            "decode": {"ms_per_token": step_ms, "tokens": max_new},
+        },
         "clocks": clocks,
     }
     if not args.skip_cpu_baseline and world == 1:

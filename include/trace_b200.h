@@ -106,6 +106,19 @@ int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps
  * TRACE_B200_MEGA_TIMING=1 in the environment when the context is created). */
 int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity);
 
+/* Frame pre-processing on the device: what process_video does per decoded frame on the host (trace/mm_utils.py:424-462):
+ * expand2square with the CLIP mean colour (:259-270), CLIPImageProcessor.preprocess (PIL bicubic resize with antialiasing,
+ * centre crop, 1/255, mean/std) and the driver's fp16 cast (evaluate.py:316).  Stateless (no ctx).
+ *   frames uint8 [F,H,W,3] RGB (device)  ->  out fp16 [F,3,crop,crop] (device)
+ * geom (host, 15 ints): canvas size, paste offset x/y, resized width/height, crop size, crop offset x/y, first canvas row
+ * and number of canvas rows the vertical pass reads, horizontal / vertical taps per output pixel, pad colour r/g/b.
+ * hbounds/vbounds [out,2] (first tap, taps) and hcoef/vcoef [out,taps] are Pillow's 22-bit fixed-point resampling tables
+ * (device, produced by trace_b200/preprocess.py exactly like Resample.c precompute_coeffs / normalize_coeffs_8bpc);
+ * mean/stdv: 3 floats (host); tmp: uint8 [F,rows,OW,3] scratch (device). */
+int trace_b200_preprocess_frames(const uint8_t* frames, int F, int H, int W, const int32_t* geom, const int32_t* hbounds,
+                                 const int32_t* hcoef, const int32_t* vbounds, const int32_t* vcoef, const float* mean,
+                                 const float* stdv, uint8_t* tmp, void* out, void* stream);
+
 /* ---- single-kernel entry points (unit-parity tests and micro-benchmarks) --------------------------- */
 int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                        const void* bias, const void* residual, int ldr, int act, int swiglu, void* stream);

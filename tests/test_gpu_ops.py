@@ -1,5 +1,6 @@
 """Single-kernel parity (through the C ABI) against plain fp32 PyTorch restatements of the same op.
 Floating-point kernels: the tolerance is stated per test (fp16 inputs/outputs, fp32 accumulation)."""
+import numpy as np
 import pytest
 import torch
 
@@ -121,3 +122,21 @@ def test_gemv(B, N, K):
         xn = gamma.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).half().float()
         wantn = xn.half().float() @ w.float().t()
         _close(E.op_gemv(w, x, gamma=gamma, eps=1e-5), wantn, 2e-3, 2e-3 * float(wantn.abs().max()), "gemv rmsnorm")
+
+
+@pytest.mark.parametrize("h,w,pad", [(360, 640, True), (480, 270, True), (336, 336, True), (240, 426, False), (1080, 1920, True)])
+def test_device_preprocess_matches_pil_chain(h, w, pad):
+    """expand2square + PIL bicubic resize + crop + normalise + fp16 on the device against the numpy restatement that is
+    pinned to Pillow / the HF PIL processor on CPU (tests/test_preprocess_cpu.py).  Integer resampling is bit-exact and
+    the float32 normalisation uses the same operation order, so the fp16 tensors must be identical."""
+    from oracle import preprocess_oracle as po
+    from trace_b200.preprocess import preprocess_frames_cuda
+    rng = np.random.default_rng(h + w)
+    frames = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    frames[1, : h // 2] = 255                                    # saturated region: bicubic overshoot must clip at 255 / 0
+    frames[1, h // 2:] = 0
+    got = preprocess_frames_cuda(torch.from_numpy(frames).cuda(), 336, aspect_ratio="pad" if pad else "none").cpu()
+    assert got.shape == (3, 3, 336, 336) and got.dtype == torch.float16
+    for f in range(3):
+        want = torch.from_numpy(po.preprocess_frame(frames[f], 336, pad=pad)).half()
+        assert torch.equal(got[f], want), f"frame {f}: {(got[f] != want).sum().item()} of {want.numel()} fp16 values differ"

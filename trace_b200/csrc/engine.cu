@@ -778,6 +778,16 @@ static int sm_count() {
   return n;
 }
 
+int trace_b200_preprocess_frames(const uint8_t* frames, int F, int H, int W, const int32_t* geom, const int32_t* hbounds,
+                                 const int32_t* hcoef, const int32_t* vbounds, const int32_t* vcoef, const float* mean,
+                                 const float* stdv, uint8_t* tmp, void* out, void* stream) {
+  TB_CHECK(frames && geom && hbounds && hcoef && vbounds && vcoef && mean && stdv && tmp && out, "null argument");
+  // geom: S, pad_x, pad_y, OW, OH, crop, crop_x, crop_y, row0, rows, hk, vk, pad_r, pad_g, pad_b
+  return preprocess_frames(frames, F, H, W, geom[0], geom[1], geom[2], geom[3], geom[4], geom[5], geom[6], geom[7], geom[8], geom[9], hbounds,
+                           hcoef, geom[10], vbounds, vcoef, geom[11], mean, stdv, geom + 12, tmp, static_cast<__half*>(out),
+                           static_cast<cudaStream_t>(stream));
+}
+
 int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K, const void* bias,
                        const void* residual, int ldr, int act, int swiglu, void* stream) {
   return gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, static_cast<__half*>(out), ldo, M, N, K,

@@ -55,6 +55,14 @@ int rope_kv_prefill(__half* qkv /*[B*S, (heads+2*kvh)*hd]*/, int B, int S, int h
                     const int32_t* block_table /*[slots,max_pages]*/, const int32_t* slot_ids /*[B]*/, int max_pages,
                     int page_size, cudaStream_t stream);
 
+// ---- preprocess.cu : expand2square + PIL bicubic resize (bit-exact integer passes) + crop + normalise + fp16 ----
+// frames uint8 [F,H,W,3]; the (virtual) padded canvas is S_w x S_h with the frame pasted at (pad_x, pad_y); resized to
+// OW x OH; centre crop `crop` at (crop_x, crop_y); tmp uint8 [F,rows,OW,3] holds canvas rows [row0, row0+rows).
+int preprocess_frames(const uint8_t* frames, int F, int H, int W, int S, int pad_x, int pad_y, int OW, int OH, int crop, int crop_x,
+                      int crop_y, int row0, int rows, const int32_t* hbounds, const int32_t* hcoef, int hk, const int32_t* vbounds,
+                      const int32_t* vcoef, int vk, const float* mean, const float* stdv, const int* pad_rgb, uint8_t* tmp, __half* out,
+                      cudaStream_t stream);
+
 // ---- decode.cu -------------------------------------------------------------------------------------------
 struct DecodeState {           // device-resident generation state (no host round trips inside the loop)
   int32_t* pos;                // [B] number of cached positions (== position id of the token being fed)

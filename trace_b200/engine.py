@@ -23,7 +23,7 @@ EXPORTS = [
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
     "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
-    "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
+    "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_weight_bytes.argtypes = [vp]
     lib.trace_b200_weight_bytes.restype = i64
     lib.trace_b200_op_gemm.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp]
+    lib.trace_b200_preprocess_frames.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), vp, vp, vp, vp,
+                                                 ctypes.POINTER(f32), ctypes.POINTER(f32), vp, vp, vp]
     lib.trace_b200_op_layernorm.argtypes = [vp, vp, vp, f32, vp, i32, i32, vp]
     lib.trace_b200_op_rmsnorm.argtypes = [vp, vp, f32, vp, i32, i32, vp]
     lib.trace_b200_op_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32,

@@ -40,9 +40,14 @@ def _read_video(path: str):
     return cap, n, fps
 
 
-def process_video(video_path, processor, aspect_ratio="pad", num_frames=NUM_FRAMES, image_grid=False, sample_scheme="uniform"):
+def process_video(video_path, processor, aspect_ratio="pad", num_frames=NUM_FRAMES, image_grid=False, sample_scheme="uniform",
+                  device=None):
     """path -> (Tensor[T,3,H,W] fp32, [[seconds]]*T).  Raises ImportError for >9999 s / negative timestamps as the
-    reference does (mm_utils.py:466-469)."""
+    reference does (mm_utils.py:466-469).
+
+    `device` (extension, default None = the reference's host path): a CUDA device; the decoded uint8 frames are uploaded
+    once and padded / resized / normalised there (csrc/preprocess.cu, bit-exact integer resampling against PIL), and the
+    returned tensor is the fp16 CUDA tensor the drivers build with `.to(dtype=torch.float16, device='cuda')`."""
     from PIL import Image
     import cv2
     if image_grid or sample_scheme != "uniform":
@@ -60,6 +65,18 @@ def process_video(video_path, processor, aspect_ratio="pad", num_frames=NUM_FRAM
         frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
     cap.release()
     stamps = [[int(i) / fps] for i in ids]
+    if stamps[-1][0] > 9999:
+        raise ImportError("The video is too long!")
+    if stamps[0][0] < 0:
+        raise ImportError("Timestamp can not be less than zero")
+    if device is not None:
+        from .preprocess import preprocess_frames_cuda
+        size = getattr(processor, "size", 336)
+        size = size if isinstance(size, int) else (size.get("shortest_edge") or size.get("height"))
+        batch = torch.from_numpy(np.stack(frames)).to(device, non_blocking=True)
+        video = preprocess_frames_cuda(batch.contiguous(), size, tuple(processor.image_mean), tuple(processor.image_std),
+                                       "pad" if aspect_ratio == "pad" else "none")
+        return video, stamps
     images = [Image.fromarray(f) for f in frames]
     if aspect_ratio == "pad":
         images = [expand2square(im, tuple(int(x * 255) for x in processor.image_mean)) for im in images]
