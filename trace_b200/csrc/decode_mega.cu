@@ -1,4 +1,4 @@
-// The whole decode step as ONE persistent kernel (one CTA per SM, 8 consumer warps + 1 producer warp):
+// The whole decode step as ONE persistent kernel (one CTA per SM: 8 consumer warps + 1 producer warp + 1 poller warp):
 //
 //   for each of the 32 layers: RMSNorm+QKV -> RoPE/KV-append/attention -> O(+residual) -> RMSNorm+gate/up(SwiGLU) -> down(+residual)
 //   then final RMSNorm + active-head logits + masked argmax, and (CTA 0) the token bookkeeping / head switch / next embedding.
@@ -9,6 +9,11 @@
 // consumer warps sit in a grid barrier or stage the next activation vector, the ring keeps filling with the next
 // phase's weights, so the weight stream is continuous across phase and layer boundaries.  Phases are separated by a
 // grid-wide barrier (atomic counter, consumers only); activations written by other CTAs are re-read with ld.global.cg.
+//
+// Structure (measured, profiles/r01_decode_ab.md): the body is ONE loop over the 4*layers+1 phases with one copy of each
+// building block and the kernel is templated on the batch bucket -- the body is re-executed for every layer, so its SASS
+// (146 KB; 354 KB when every phase was an inlined copy) has to stay in the instruction cache.  Consumers copy a ring stage
+// into registers, release it, then run the mma.sync chain.  Optional TMEM weight reservoir (off by default): see below.
 //
 // Replaces: trace_mistral.py:114-264 forward (decoder layers via HF MistralModel, heads :190-200, mask :244-252),
 // :336-344 head switch, trace_arch.py:345-375 embedding dispatch, HF greedy argmax -- for one generated token.
