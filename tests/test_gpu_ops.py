@@ -105,6 +105,32 @@ def test_attention(B, S, heads, kvh, hd, causal, impl):
     _close(out, want, 5e-3, 5e-3, f"attention B{B} S{S} h{heads}/{kvh} d{hd} causal={causal}")
 
 
+@pytest.mark.parametrize("S,hd,causal", [(577, 64, False), (900, 128, True)])
+def test_attention_tcgen05_lazy_rescale(S, hd, causal):
+    """Peaky scores (|s| up to ~40): the running maximum of a row grows by more than 2^8 between key tiles, so the
+    TMEM-resident O accumulator and the row sum are rescaled in place (tcgen05.ld -> mul -> tcgen05.st); rows whose
+    maximum moves by less keep their stale reference.  Both paths must agree with fp32 softmax."""
+    from trace_b200 import engine as E
+    heads, kvh, B = 4, 4, 2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn((B, S, (heads + 2 * kvh) * hd), generator=g, device="cuda")
+    qkv[..., : heads * hd] *= 3.0                       # q
+    qkv[..., heads * hd: (heads + kvh) * hd] *= 3.0     # k
+    # make late keys win for half of the rows: the maximum keeps growing along the key axis
+    qkv[:, S // 2:, heads * hd: (heads + kvh) * hd] *= 1.5
+    qkv = qkv.half()
+    out = E.op_attention_tc(qkv, heads, kvh, hd, causal)
+    torch.cuda.synchronize()
+    q = qkv[..., : heads * hd].float().view(B, S, heads, hd).transpose(1, 2)
+    k = qkv[..., heads * hd: (heads + kvh) * hd].float().view(B, S, kvh, hd).transpose(1, 2)
+    v = qkv[..., (heads + kvh) * hd:].float().view(B, S, kvh, hd).transpose(1, 2)
+    s_ = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    if causal:
+        s_ = s_.masked_fill(torch.triu(torch.ones(S, S, device="cuda", dtype=torch.bool), 1), float("-inf"))
+    want = (torch.softmax(s_, -1) @ v).transpose(1, 2).reshape(B, S, heads * hd)
+    _close(out, want, 1e-2, 1e-2, f"attention tcgen05 lazy rescale S{S} d{hd}")
+
+
 @pytest.mark.parametrize("B,N,K", [(1, 4096, 4096), (3, 6144, 4096), (8, 4096, 14336), (2, 512, 256), (1, 4096, 512)])
 def test_gemv(B, N, K):
     from trace_b200 import engine as E

@@ -1,19 +1,22 @@
 // Blackwell-native attention forward: softmax(Q K^T * scale) V with both contractions on tcgen05 tensor cores,
-// operands fed by TMA, S = Q K^T and P V accumulators in TMEM.
+// operands fed by TMA, S = Q K^T and the output accumulator O in TMEM.
 //   * ViT:     HF CLIPAttention (non-causal, 16 heads x 64, n = 577)            -- clip_encoder.py:50
 //   * prefill: HF MistralAttention (causal, GQA 32 q / 8 kv heads x 128)        -- trace_mistral.py:178
 //
 // One CTA = one 128-row query tile of one (batch, head).  Roles (192 threads):
-//   warp 4 : TMA producer -- Q once, then K / V tiles of 128 keys into a 2-stage ring (boxes {64 x 128}, SWIZZLE_128B,
+//   warp 4 : TMA producer -- Q once, then K and V tiles of 128 keys into two 2-stage rings (boxes {64 x 128}, SWIZZLE_128B,
 //            straight out of the fused qkv activation: no transposes, no per-head copies)
 //   warp 5 : UMMA issuer  -- S[128x128] = Q K^T   (tcgen05.mma kind::f16, M=128 N=128, A/B K-major)        -> TMEM cols [0,128)
-//                            PV[128xd]  = P V     (M=128 N=d K=128; P from smem (K-major), V as an MN-major B operand,
+//                            O[128xd] += P V      (M=128 N=d K=128; P from smem (K-major), V as an MN-major B operand,
 //                                                  i.e. the [key][d] tile exactly as TMA wrote it)          -> TMEM cols [128,128+d)
-//   warps 0-3 : softmax + output (thread = query row): tcgen05.ld S -> scale / mask -> running max / sum (fp32, exp2)
-//            -> P (fp16, as the reference rounds softmax before the PV matmul) written to smem in the swizzled K-major
-//            layout UMMA expects -> fence.proxy.async -> after the PV MMA: O = O*corr + PV in registers.
-// The d=64 (ViT) instantiation uses 112 KB of smem and 256 TMEM columns, so two CTAs share an SM and one CTA's softmax
-// overlaps the other's MMAs; d=128 runs one CTA per SM.
+//            software-pipelined: S(j) is issued as soon as the softmax warps hold S(j-1) in registers, i.e. it runs
+//            under the exponentials of tile j-1; O += P(j-1) V(j-1) follows when P(j-1) is in shared memory.
+//   warps 0-3 : softmax (thread = query row): ONE tcgen05.ld of the 128 scores into registers -> release the S buffer ->
+//            running max with LAZY rescale (O and the row sum are only rescaled when the max grows by more than 2^8, so
+//            the accumulator stays in TMEM and is touched by these warps only then and in the epilogue) -> ex2 ->
+//            P (fp16, as the reference rounds softmax before the PV matmul) into the swizzled K-major layout UMMA expects.
+// The d=64 (ViT) instantiation uses 112 KB of smem and 256 TMEM columns, so two CTAs share an SM (the ViT tile loop is
+// only 5 long and exp-bound: the second CTA hides the first one's load / drain bubbles); d=128 runs one CTA per SM.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -45,14 +48,20 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int b_mn_major) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, HD == 64 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O, int seqlen, int o_stride, int64_t o_bstride,
                int q_col0, int k_col0, int v_col0, int group, float scale_log2) {
   constexpr int NA = HD / 64;                       // 64-column atoms per head row
   constexpr int Q_BYTES = NA * ATOM_BYTES;
   constexpr int KV_BYTES = NA * ATOM_BYTES;
-  constexpr int TMEM_COLS = 256;                    // S: [0,128)  PV: [128, 128+HD)
+  constexpr int TMEM_COLS = 256;                    // S: [0,128)  O: [128, 128+HD)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -61,12 +70,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
   uint8_t* sP = sV + 2 * KV_BYTES;                  // 2 atoms (128 keys)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATOM_BYTES);
   uint64_t* q_full = bars;                          // [1]
-  uint64_t* kv_full = bars + 1;                     // [2]
-  uint64_t* kv_empty = bars + 3;                    // [2]
-  uint64_t* s_full = bars + 5;                      // [1]
-  uint64_t* p_full = bars + 6;                      // [1]
-  uint64_t* pv_full = bars + 7;                     // [1]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;                      // [2]
+  uint64_t* k_empty = bars + 3;                     // [2]
+  uint64_t* v_full = bars + 5;                      // [2]
+  uint64_t* v_empty = bars + 7;                     // [2]
+  uint64_t* s_full = bars + 9;                      // [1] S(j) complete in TMEM
+  uint64_t* s_free = bars + 10;                     // [1] S(j) is in the softmax warps' registers
+  uint64_t* p_full = bars + 11;                     // [1] P(j) in shared memory, O rescaled
+  uint64_t* pv_done = bars + 12;                    // [1] O += P(j) V(j) complete
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -78,10 +90,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
   if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap);
   if (warp == 5 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_base_ptr, TMEM_COLS);
@@ -99,136 +112,160 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       const int kvh = h / group;
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        mbar_wait(&k_empty[st], par);
+        mbar_expect_tx(&k_full[st], KV_BYTES);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) {
-          tma_load_2d(sK + st * KV_BYTES + a * ATOM_BYTES, &tmap, &kv_full[st], k_col0 + kvh * HD + a * 64, row_base + j * AT_BKV);
-          tma_load_2d(sV + st * KV_BYTES + a * ATOM_BYTES, &tmap, &kv_full[st], v_col0 + kvh * HD + a * 64, row_base + j * AT_BKV);
-        }
+        for (int a = 0; a < NA; ++a)
+          tma_load_2d(sK + st * KV_BYTES + a * ATOM_BYTES, &tmap, &k_full[st], k_col0 + kvh * HD + a * 64, row_base + j * AT_BKV);
+        mbar_wait(&v_empty[st], par);
+        mbar_expect_tx(&v_full[st], KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_2d(sV + st * KV_BYTES + a * ATOM_BYTES, &tmap, &v_full[st], v_col0 + kvh * HD + a * 64, row_base + j * AT_BKV);
       }
     }
   } else if (warp == 5) {
     // ===================== UMMA issuer =====================
     constexpr uint32_t idesc_s = idesc_f16(128, AT_BKV, 0);       // S = Q K^T : both operands K-major
-    constexpr uint32_t idesc_pv = idesc_f16(128, HD, 1);          // PV = P V  : V is MN-major ([key][d] rows)
+    constexpr uint32_t idesc_pv = idesc_f16(128, HD, 1);          // O += P V  : V is MN-major ([key][d] rows)
     mbar_wait(q_full, 0);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
+    for (int j = 0; j <= n_tiles; ++j) {
+      if (j < n_tiles) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);                // S(j-1) has left TMEM
+        tc_fence_after();
+        if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(sQ + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
-          const uint64_t bd = umma_desc_sw128(smem_u32(sK + st * KV_BYTES + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
-          umma_f16(tmem_base, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint64_t ad = umma_desc_sw128(smem_u32(sQ + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
+            const uint64_t bd = umma_desc_sw128(smem_u32(sK + st * KV_BYTES + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
+            umma_f16(tmem_base, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);
         }
-        umma_commit(s_full);
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(p_full, j & 1);                                   // P(j) is in shared memory, S(j) has been read
-      tc_fence_after();
-      if (lane == 0) {
+      if (j > 0) {
+        const int i = j - 1, st = i & 1;
+        mbar_wait(p_full, i & 1);                                 // P(i) is in shared memory, O is rescaled
+        mbar_wait(&v_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
 #pragma unroll
-        for (int kk = 0; kk < AT_BKV / 16; ++kk) {                 // 16 keys per MMA
-          const uint64_t ad = umma_desc_sw128(smem_u32(sP + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
-          const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV + st * KV_BYTES) + kk * 2048, ATOM_BYTES);
-          umma_f16(tmem_base + 128, ad, bd, idesc_pv, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < AT_BKV / 16; ++kk) {              // 16 keys per MMA
+            const uint64_t ad = umma_desc_sw128(smem_u32(sP + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
+            const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV + st * KV_BYTES) + kk * 2048, ATOM_BYTES);
+            umma_f16(tmem_base + 128, ad, bd, idesc_pv, (i > 0 || kk != 0) ? 1u : 0u);
+          }
+          umma_commit(pv_done);
+          umma_commit(&v_empty[st]);
         }
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===================== softmax + output (thread = query row) =====================
+    // ===================== softmax (thread = query row) =====================
     const int r = warp * 32 + lane;                               // TMEM lane == row of the tile
     const int qrow = q0 + r;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float o_acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;                         // m_run: (possibly stale) reference maximum of the row
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kbase = j * AT_BKV;
-      // ---- pass A: row maximum ----
+      uint32_t v[128];
+      tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_32x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld_32x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                                        // the issuer may overwrite S with tile j+1
+      const bool masked = (kbase + AT_BKV > seqlen) || (CAUSAL && kbase + AT_BKV - 1 > q0);
+      if (masked) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const int col = kbase + i;
+          if (!(col < seqlen && (!CAUSAL || col <= qrow))) v[i] = __float_as_uint(-INFINITY);
+        }
+      }
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = kbase + c * 32 + i;
-          const bool ok = col < seqlen && (!CAUSAL || col <= qrow);
-          if (ok) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      // lazy rescale: keep the old reference maximum unless the new one is more than 2^8 above it (P stays <= 256 in fp16,
+      // the row sum and O stay consistent with the reference that was used for every term)
+      bool grow = false;
+      float corr = 1.f;
+      if (j == 0) {
+        m_run = mx;
+      } else if ((mx - m_run) * scale_log2 > 8.f) {
+        grow = true;
+        corr = ex2_approx((m_run - mx) * scale_log2);
+        m_run = mx;
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);                          // P buffer is free again, O holds tiles < j
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(taddr + 128 + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st_32x32(taddr + 128 + c * 32, o);
+          }
+          tmem_st_wait();
+          l_run *= corr;
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float ms = (m_new == -INFINITY) ? 0.f : m_new * scale_log2;
-      const float corr = exp2f(m_run * scale_log2 - ms);
-      // ---- pass B: P = exp2(S*scale - max) -> fp16 -> swizzled K-major smem ----
+      const float ms = (m_run == -INFINITY) ? 0.f : m_run * scale_log2;
       float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      uint8_t* prow = sP + r * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = kbase + c * 32 + 2 * i;
-          const bool ok0 = col < seqlen && (!CAUSAL || col <= qrow);
-          const bool ok1 = col + 1 < seqlen && (!CAUSAL || col + 1 <= qrow);
-          const float p0 = ok0 ? exp2f(__uint_as_float(v[2 * i]) * scale_log2 - ms) : 0.f;
-          const float p1 = ok1 ? exp2f(__uint_as_float(v[2 * i + 1]) * scale_log2 - ms) : 0.f;
+      for (int c = 0; c < 16; ++c) {                              // 8 keys -> one 16-byte chunk of the swizzled row
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 8 + 2 * q]), scale_log2, -ms));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 8 + 2 * q + 1]), scale_log2, -ms));
           rs += p0 + p1;
-          pk[i] = pack_half2(p0, p1);
+          pk[q] = pack_half2(p0, p1);
         }
-        uint8_t* prow = sP + (c >> 1) * ATOM_BYTES + r * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l_run = l_run * corr + rs;
-      m_run = m_new;
+      l_run += rs;
       tc_fence_before();
       fence_proxy_async();                                        // generic-proxy smem writes -> visible to the UMMA
       mbar_arrive(p_full);
-#pragma unroll
-      for (int i = 0; i < HD; ++i) o_acc[i] *= corr;
-      // ---- O += P V ----
-      mbar_wait(pv_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + 128 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(v[i]);
-      }
-      tc_fence_before();
     }
-    if (qrow < seqlen) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __half* op = O + b * o_bstride + static_cast<int64_t>(qrow) * o_stride + h * HD;
+    // ---- epilogue: O / l -> fp16 ----
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __half* op = O + b * o_bstride + static_cast<int64_t>(qrow) * o_stride + h * HD;
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        uint4 o;
-        o.x = pack_half2(o_acc[i * 8 + 0] * inv, o_acc[i * 8 + 1] * inv);
-        o.y = pack_half2(o_acc[i * 8 + 2] * inv, o_acc[i * 8 + 3] * inv);
-        o.z = pack_half2(o_acc[i * 8 + 4] * inv, o_acc[i * 8 + 5] * inv);
-        o.w = pack_half2(o_acc[i * 8 + 6] * inv, o_acc[i * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(op + i * 8) = o;
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(taddr + 128 + c * 32, o);
+      tmem_ld_wait();
+      if (qrow < seqlen) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_half2(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv);
+          w.y = pack_half2(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv);
+          w.z = pack_half2(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv);
+          w.w = pack_half2(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+        }
       }
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
