@@ -176,25 +176,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kbase = j * AT_BKV;
-      uint32_t v[128];
-      tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      tmem_ld_32x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
-      tmem_ld_32x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);                                        // the issuer may overwrite S with tile j+1
       const bool masked = (kbase + AT_BKV > seqlen) || (CAUSAL && kbase + AT_BKV - 1 > q0);
-      if (masked) {
+      // d = 128 runs one CTA per SM and can afford the whole score row in registers (ONE TMEM read); d = 64 shares the SM
+      // between two CTAs (170 registers per thread): two passes over TMEM in 32-column chunks instead of spilling.
+      constexpr bool ONE_PASS = HD == 128;
+      constexpr int NV = ONE_PASS ? 128 : 64;
+      uint32_t v[NV];
+      float mx = -INFINITY;
+      if (ONE_PASS) {
+        tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
+        tmem_ld_32x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64 % NV]));
+        tmem_ld_32x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96 % NV]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);                                      // the issuer may overwrite S with tile j+1
+        if (masked) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const int col = kbase + i;
-          if (!(col < seqlen && (!CAUSAL || col <= qrow))) v[i] = __float_as_uint(-INFINITY);
+          for (int i = 0; i < NV; ++i) {
+            const int col = kbase + i;
+            if (!(col < seqlen && (!CAUSAL || col <= qrow))) v[i] = __float_as_uint(-INFINITY);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
+          tmem_ld_wait();
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              const int col = kbase + c * 64 + i;
+              if (col < seqlen && (!CAUSAL || col <= qrow)) mx = fmaxf(mx, __uint_as_float(v[i % NV]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i % NV]));
+          }
         }
       }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       // lazy rescale: keep the old reference maximum unless the new one is more than 2^8 above it (P stays <= 256 in fp16,
       // the row sum and O stay consistent with the reference that was used for every term)
       bool grow = false;
@@ -226,17 +249,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       const float ms = (m_run == -INFINITY) ? 0.f : m_run * scale_log2;
       float rs = 0.f;
       uint8_t* prow = sP + r * 128;
+      if (ONE_PASS) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {                              // 8 keys -> one 16-byte chunk of the swizzled row
-        uint32_t pk[4];
+        for (int c = 0; c < 16; ++c) {                            // 8 keys -> one 16-byte chunk of the swizzled row
+          uint32_t pk[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 8 + 2 * q]), scale_log2, -ms));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 8 + 2 * q + 1]), scale_log2, -ms));
-          rs += p0 + p1;
-          pk[q] = pack_half2(p0, p1);
+          for (int q = 0; q < 4; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[(c * 8 + 2 * q) % NV]), scale_log2, -ms));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[(c * 8 + 2 * q + 1) % NV]), scale_log2, -ms));
+            rs += p0 + p1;
+            pk[q] = pack_half2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          tmem_ld_32x32(taddr + c2 * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(taddr + c2 * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
+          tmem_ld_wait();
+          if (c2 == 1) {
+            tc_fence_before();
+            mbar_arrive(s_free);                                  // last read of S(j)
+          }
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const int c = c2 * 8 + cc;
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = kbase + c * 8 + 2 * q;
+              float s0 = __uint_as_float(v[(cc * 8 + 2 * q) % NV]), s1 = __uint_as_float(v[(cc * 8 + 2 * q + 1) % NV]);
+              if (masked) {
+                if (!(col < seqlen && (!CAUSAL || col <= qrow))) s0 = -INFINITY;
+                if (!(col + 1 < seqlen && (!CAUSAL || col + 1 <= qrow))) s1 = -INFINITY;
+              }
+              const float p0 = ex2_approx(fmaf(s0, scale_log2, -ms));
+              const float p1 = ex2_approx(fmaf(s1, scale_log2, -ms));
+              rs += p0 + p1;
+              pk[q] = pack_half2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
       }
       l_run += rs;
       tc_fence_before();
