@@ -179,7 +179,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       const bool masked = (kbase + AT_BKV > seqlen) || (CAUSAL && kbase + AT_BKV - 1 > q0);
       // d = 128 runs one CTA per SM and can afford the whole score row in registers (ONE TMEM read); d = 64 shares the SM
       // between two CTAs (170 registers per thread): two passes over TMEM in 32-column chunks instead of spilling.
-      constexpr bool ONE_PASS = HD == 128;
+      constexpr bool ONE_PASS = true;
       constexpr int NV = ONE_PASS ? 128 : 64;
       uint32_t v[NV];
       float mx = -INFINITY;
@@ -233,14 +233,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
         mbar_wait(pv_done, (j - 1) & 1);                          // P buffer is free again, O holds tiles < j
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(taddr + 128 + c * 32, o);
+          // rare (the maximum of some row of this warp grew by more than 2^8): 16-column chunks keep the temporaries small
+          // next to the 128 live scores
+#pragma unroll 1
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(taddr + 128 + c * 16, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            tmem_st_32x32(taddr + 128 + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st_32x16(taddr + 128 + c * 16, o);
           }
           tmem_st_wait();
           l_run *= corr;
