@@ -62,8 +62,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
   constexpr int Q_BYTES = NA * ATOM_BYTES;
   constexpr int KV_BYTES = NA * ATOM_BYTES;
   constexpr int TMEM_COLS = 256;                    // S: [0,128)  O: [128, 128+HD)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) comes from the declaration, not from a padded request: with the pad the
+  // d = 64 instantiation needed 113.1 KB + 1 KB reserved per CTA and exactly missed two CTAs per SM (228 KB)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;                       // 2 stages
   uint8_t* sV = sK + 2 * KV_BYTES;                  // 2 stages
@@ -347,7 +350,7 @@ EncodeTiledFn at_encode_fn() {
 template <int HD, bool CAUSAL>
 int launch_tc(const CUtensorMap& tm, __half* O, int seqlen, int o_stride, int64_t o_bstride, int q_col0, int k_col0, int v_col0,
               int heads, int group, int batch, float scale, cudaStream_t stream) {
-  constexpr int SMEM = (HD / 64) * ATOM_BYTES * 5 + 2 * ATOM_BYTES + 1024 + 128;
+  constexpr int SMEM = (HD / 64) * ATOM_BYTES * 5 + 2 * ATOM_BYTES + 128;
   static bool attr_set = false;
   if (!attr_set) {
     TB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
