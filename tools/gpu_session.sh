@@ -11,10 +11,10 @@ for f in tests/test_gpu_ops.py tests/test_gpu_e2e.py tests/test_gpu_serving.py; 
 done
 timeout 200 python tools/bench_kernels.py > gpurun_out/kernel_microbench.txt 2>&1; tail -14 gpurun_out/kernel_microbench.txt
 timeout 500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; cat gpurun_out/bench_n1.json
-TRACE_B200_ATTN_TC=1 timeout 300 python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_n1_attn_tc.json 2> gpurun_out/bench_n1_attn_tc.err; echo "bench(attn tc) exit $?"
+TRACE_B200_ATTN_TC=0 timeout 300 python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_n1_attn_mma.json 2> gpurun_out/bench_n1_attn_mma.err; echo "bench(mma.sync attention) exit $?"
 python - <<'PY'
 import json
-for n in ("bench_n1", "bench_n1_attn_tc"):
+for n in ("bench_n1", "bench_n1_attn_mma"):
     try:
         j = json.loads(open(f"gpurun_out/{n}.json").read().strip().splitlines()[-1])
         print(n, "events/s", round(j["value"], 3), "e2e", round(j["e2e"]["value"], 3), "ms/decode", round(j["roofline"]["ms_per_decode_step"], 4),
