@@ -108,7 +108,7 @@ __device__ __forceinline__ void relay_one(Stream& st, const StreamTab& tab, cons
   stream_skip_empty(st, tab);
 }
 
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, const GvSmem& m, int stages) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, const GvSmem& m, int stages, bool allow) {
   cons_sync();
   target += gridDim.x;
   if (threadIdx.x == 0) {
@@ -130,7 +130,7 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, Strea
   for (int it = 0;; ++it) {
     if (threadIdx.x == 0) {
       int code = 0;
-      const bool can = st.tm_count < TM_SLOTS && st.seq_left > 0;
+      const bool can = allow && st.tm_count < TM_SLOTS && st.seq_left > 0;
       if (tab.released == target && (!can || --patience < 0)) code = 2;   // leave as soon as the grid is through
       else if (can && mbar_test(&m.full[st.s], st.ph)) code = 1;
       if (code == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // the poller's acquire, made ours before the CTA barrier
@@ -349,6 +349,7 @@ struct MegaParams {
   int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
   int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
   int part_bytes, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
+  int relay_sites;                    // bit t: the barrier before phase type t parks stages (bit 5: the one before attention)
   int early_release;                  // hand a ring stage back before (1) or after (0) its MMA chain
   int max_inflight;                   // producer request throttle in stages (0 = the whole ring)
   int tm_relay;                       // park ring stages in TMEM while waiting in grid barriers (0 = off)
@@ -770,8 +771,8 @@ __device__ __forceinline__ void phase_epilogue(const GvSmem& m, int r0, int r1, 
 // One copy of the barrier + relay code for all call sites.  `m` is passed BY VALUE: taking its address would force the
 // kernel's copy into local memory and every shared-memory access derived from it (the whole consume loop) would be
 // compiled as a generic LD/ST instead of LDS/STS.
-__device__ __noinline__ void grid_sync_shared(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, GvSmem m, int stages) {
-  grid_sync(bar, target, st, tab, m, stages);
+__device__ __noinline__ void grid_sync_shared(unsigned* bar, unsigned& target, Stream& st, StreamTab& tab, GvSmem m, int stages, bool allow) {
+  grid_sync(bar, target, st, tab, m, stages, allow);
 }
 
 template <int NB>
@@ -879,7 +880,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
     GammaRegs gm;
     if (pro) gm = load_gamma(type == 0 ? L.ln1 : type == 2 ? L.ln2 : p.final_norm, p.H);
     if (type == 0) attn_prefetch(p, L, *ctl);
-    if (seq > 0) grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);      // the phase's input vector is complete
+    if (seq > 0) grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages, (p.relay_sites >> type) & 1);   // the phase's input vector is complete
     stamp(p, l, type * 2 + (type > 0 ? 2 : 0));
     int r0, r1;
     cta_rows(g.N, r0, r1);
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
       phase_epilogue<NB>(m, r0, r1, p.B, out, type == 0 ? p.qkvw : type == 2 ? p.ffn : p.H, type == 2 ? 2 : (type == 0 ? 0 : 1));
       stamp(p, l, type * 2 + (type > 0 ? 3 : 1));
       if (type == 0) {
-        grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);               // q, k, v complete
+        grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages, (p.relay_sites >> 5) & 1);   // q, k, v complete
         stamp(p, l, 2);
         if (ctl->valid) attn_item(p, L, *ctl, m.s_part, l, &s_gate);
         else if (threadIdx.x == 0) s_gate = l + 1;
@@ -954,7 +955,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_kernel(const __grid
       }
     }
   }
-  grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages);
+  grid_sync_shared(p.gbar, target, st, s_tab, m, p.stages, false);
   if (blockIdx.x == 0) finalize_step(p, ncta);
   // exit protocol: the last CTA to leave resets the barrier counters for the next launch
   cons_sync();
@@ -1054,7 +1055,7 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
   p.pf_ahead = a.pf_ahead; p.pf_gap_kb = a.pf_gap_kb; p.pf_attn_kb = a.pf_attn_kb;
   p.tm_relay = a.tm_relay; p.gate_mode = a.gate_mode;
-  p.max_inflight = a.max_inflight; p.early_release = a.early_release;
+  p.max_inflight = a.max_inflight; p.early_release = a.early_release; p.relay_sites = a.relay_sites;
   p.dbg = a.dbg;
   int kpks[10];
   size_t smem = 0;

@@ -91,7 +91,7 @@ struct trace_b200_ctx {
   unsigned* d_gbar = nullptr;
   unsigned long long* d_dbg = nullptr;
   bool fused_decode = true;
-  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, pf_gap_kb = 0, pf_attn_kb = 0, max_inflight = 0, early_release = 1, max_stages = 4;   // fused decode-step switches (kernels.h)
+  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, pf_gap_kb = 0, pf_attn_kb = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
   bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
 };
 
@@ -246,6 +246,7 @@ int allocate_all(trace_b200_ctx* ctx) {
     ctx->max_inflight = env_int("TRACE_B200_INFLIGHT", 0, 3, 0);
     ctx->early_release = env_int("TRACE_B200_EARLY_REL", 0, 1, 1);
     ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 4);
+    ctx->relay_sites = env_int("TRACE_B200_TM_SITES", 0, 63, 63);
     const char* env2 = getenv("TRACE_B200_ATTN_TC");
     ctx->attn_tc = (env2 != nullptr) ? atoi(env2) == 1 : true;   // tcgen05 attention: 2.0x (ViT) / 2.6x (prefill) the mma.sync kernel
   }
@@ -456,7 +457,7 @@ int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out,
     a.part_ml = ctx->d_part_ml; a.counters = ctx->d_counters; a.cand_val = ctx->d_cand_val; a.cand_idx = ctx->d_cand_idx;
     a.logits_out = logits_out; a.embed = ctx->embed; a.time_tab = ctx->time_tab; a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab;
     a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar; a.dbg = ctx->d_dbg;
-    a.tm_relay = ctx->tm_relay; a.gate_mode = ctx->gate_mode; a.pf_ahead = ctx->pf_ahead; a.pf_gap_kb = ctx->pf_gap_kb; a.pf_attn_kb = ctx->pf_attn_kb; a.max_inflight = ctx->max_inflight; a.early_release = ctx->early_release; a.max_stages = ctx->max_stages;
+    a.tm_relay = ctx->tm_relay; a.gate_mode = ctx->gate_mode; a.pf_ahead = ctx->pf_ahead; a.pf_gap_kb = ctx->pf_gap_kb; a.pf_attn_kb = ctx->pf_attn_kb; a.max_inflight = ctx->max_inflight; a.early_release = ctx->early_release; a.max_stages = ctx->max_stages; a.relay_sites = ctx->relay_sites;
     RUN(decode_step_fused(a, s));
     return 0;
   }
