@@ -485,8 +485,11 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
         vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
       }
     }
+    // the LAST pass's latency-critical requests are out: the producer may start the O weights.  (With several passes per
+    // CTA -- batch 4..8: 500-1000 keys per work item -- opening the gate after the first pass put every later pass behind
+    // the weight stream's 3 us queue: 5.5 us per pass instead of ~1.5.)
+    if (tid == 0 && base + GV_WARPS * 16 >= nloc) *gate = dl + 1;
     if (first) {
-      if (tid == 0) *gate = dl + 1;          // latency-critical requests are out: the producer may start the O weights
       cons_sync();                            // qs / knew / vnew visible
       stamp(p, dl, 20);
       first = false;
@@ -984,6 +987,10 @@ struct MegaPlan {
 };
 
 static int pick_kp_cap(int K, int B, size_t cap_bytes) {
+  // prefer k-phases made of full 1024-column stages (32 KB in flight per ring slot): at batch 8 the down projection used
+  // to get KP = 3584 -> KS = 512, i.e. half-filled slots and a latency-bound stream (53 us instead of ~20)
+  for (int kp = 16384; kp >= 1024; kp -= 1024)
+    if (K % kp == 0 && kp <= K && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= cap_bytes) return kp;
   for (int kp = 16384; kp >= 256; kp -= 256)
     if (K % kp == 0 && kp <= K && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= cap_bytes) return kp;
   return 0;
