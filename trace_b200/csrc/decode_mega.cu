@@ -467,35 +467,28 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   for (int h = 0; h < MG_G; ++h) { m_w[h] = -INFINITY; l_w[h] = 0.f; o_w[h][0] = o_w[h][1] = o_w[h][2] = o_w[h][3] = 0.f; }
   const int hf = lane & 1;
   bool first = true;
-  // Rotated software pipeline over the passes (128 keys each) with no extra registers: the K rows of pass p+1 are
-  // requested as soon as the scores of pass p are computed (kreg is dead), the V rows of pass p+1 after the PV product of
-  // pass p (vreg is dead).  One pass at batch 1; 4-8 at batch 4..8, where every pass used to pay a full memory round trip.
-  uint4 kreg[8];
-  uint2 vreg[16];
-  auto load_k = [&](int base) {
-    const int jk = base + warp * 16 + (lane >> 1);
-    const int key = start + (jk < nloc ? jk : 0);
-    const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
-  };
-  auto load_v = [&](int base) {
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int j = base + warp * 16 + u;
-      const int keyv = start + (j < nloc ? j : 0);
-      vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
-    }
-  };
-  load_k(0);
-  load_v(0);
   for (int base = 0; base < nloc || first; base += GV_WARPS * 16) {
+    // ---- request this pass's rows: K half row of key (warp*16 + lane/2), V 4-dim slices of the warp's 16 keys ----
     const int jk = base + warp * 16 + (lane >> 1);
     const bool kvalid = jk < nloc;
-    const bool more = base + GV_WARPS * 16 < nloc;
-    // the LAST pass's latency-critical requests are out: the producer may start the O weights (opening the gate earlier
-    // puts the remaining passes behind the weight stream's queue)
-    if (tid == 0 && !more) *gate = dl + 1;
+    uint4 kreg[8];
+    uint2 vreg[16];
+    {
+      const int key = start + (kvalid ? jk : 0);
+      const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int j = base + warp * 16 + u;
+        const int keyv = start + (j < nloc ? j : 0);
+        vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
+      }
+    }
+    // the LAST pass's latency-critical requests are out: the producer may start the O weights.  (With several passes per
+    // CTA -- batch 4..8: 500-1000 keys per work item -- opening the gate after the first pass put every later pass behind
+    // the weight stream's 3 us queue: 5.5 us per pass instead of ~1.5.)
+    if (tid == 0 && base + GV_WARPS * 16 >= nloc) *gate = dl + 1;
     if (first) {
       cons_sync();                            // qs / knew / vnew visible
       stamp(p, dl, 20);
@@ -515,7 +508,6 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
         acc[h] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
       }
     }
-    if (more) load_k(base + GV_WARPS * 16);
 #pragma unroll
     for (int h = 0; h < MG_G; ++h) {
       acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
@@ -545,7 +537,6 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
         o_w[h][0] += pr * v0.x; o_w[h][1] += pr * v0.y; o_w[h][2] += pr * v1.x; o_w[h][3] += pr * v1.y;
       }
     }
-    if (more) load_v(base + GV_WARPS * 16);
   }
   if (split == 0 && warp == 0) {   // the token being decoded attends to itself: key/value from shared memory, not the cache
 #pragma unroll
