@@ -37,29 +37,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // executed by the 256 consumer threads only.  Activations are read with ld.global.cg (other CTAs rewrite them
 // between the phases of the fused decode step).
 __device__ __forceinline__ void stage_x_plain(__half* xs, const __half* x, int ldx, int B, int k0, int KP) {
-  // all (row, 16-byte chunk) pairs flattened over the 256 threads, 8 loads in flight per thread: with a loop over the
-  // batch rows outside, every row cost its own dependent L2 round trip (4 us per staging at batch 8)
   const int pitch = KP + XS_PAD;
-  const int per = KP / 8, total = B * per;
-  for (int base = 0; base < total; base += GV_CONS * 8) {
-    uint4 r[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int idx = base + k * GV_CONS + threadIdx.x;
-      if (idx < total) {
-        const int b = idx / per, i = idx - b * per;
-        r[k] = __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8));
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int idx = base + k * GV_CONS + threadIdx.x;
-      if (idx < total) {
-        const int b = idx / per, i = idx - b * per;
-        *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = r[k];
-      }
-    }
-  }
+  for (int b = 0; b < B; ++b)
+    for (int i = threadIdx.x; i < KP / 8; i += GV_CONS)
+      *reinterpret_cast<uint4*>(xs + b * pitch + i * 8) = __ldcg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * ldx + k0 + i * 8));
 }
 
 // RMSNorm weights of this thread's columns: a weight, so it can be fetched BEFORE the activations exist (before the
