@@ -107,3 +107,60 @@ def test_scheduler_buckets_mixed_clips_and_reuses_encodes():
     for k, (dev, host, ts, ps) in enumerate(spec):
         _check_row(res[k].ids.tolist(), o, _prompt(10, ps), host, ts, 1, 16, f"request {k}")
         assert res[k].head in (0, 1, 2)
+
+
+def test_early_eos_rows_emit_pad_and_loop_stops():
+    """HF greedy semantics (SURVEY §9-11): a row that emitted EOS keeps emitting pad_token_id while the other rows continue;
+    the loop stops when every row has finished.  EOS is chosen from the oracle's own output so that row 0 stops early."""
+    d = synth.tiny_dims(4)
+    model = _model(d, 3)
+    o = orc.TraceOracle(d, synth.make_state_dict(d, 3))
+    clips, stamps, prompts, free_run = [], [], [], []
+    for b in range(2):
+        px, ts = synth.synthetic_clip(d, 4, seed=200 + b, duration_s=40.0)
+        clips.append(px)
+        stamps.append(ts)
+        prompts.append(_prompt(10, 70 + b))
+        free_run.append(o.generate(prompts[b], px.float(), ts, head=1, max_new_tokens=12))
+    # an id that row 0 emits at step >= 2 and that row 1 does not emit before that step
+    eos = step0 = None
+    for s in range(2, 12):
+        if free_run[0][s] not in free_run[1][: s + 1]:
+            eos, step0 = free_run[0][s], s
+            break
+    if eos is None:
+        pytest.skip("the two rows emit the same ids (degenerate synthetic weights)")
+    ids = torch.tensor(prompts, dtype=torch.int64, device="cuda")
+    heads = [1, 1]
+    pad = 7
+    out = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=[c.cuda() for c in clips], modal_list=["video"] * 2,
+                         video_timestamps=stamps, heads=heads, do_sample=False, max_new_tokens=12, pad_token_id=pad, eos_token_id=eos)
+    want1 = o.generate(prompts[1], clips[1].float(), stamps[1], head=1, max_new_tokens=12, eos=eos, pad=pad)
+    row0, row1 = out[0].tolist(), out[1].tolist()
+    first = row0.index(eos)
+    assert first <= step0 and row0[:first + 1] == free_run[0][:first + 1]
+    assert all(t == pad for t in row0[first + 1:]), row0
+    assert row1[: len(want1)] == want1
+    assert out.shape[1] == len(want1) or out.shape[1] == 12
+
+
+def test_engine_errors_are_loud():
+    from trace_b200.engine import Engine, TraceB200Error
+    d = synth.tiny_dims(4)
+    eng = Engine(d, device=0, vit_chunk_frames=4, max_prefill_tokens=256, max_ctx=128, kv_pages=3)
+    eng.load_state_dict(synth.iter_state_dict(d, 0))
+    with pytest.raises(TraceB200Error):
+        eng.alloc_slot(129)                      # longer than max_ctx
+    a = eng.alloc_slot(128)                      # 2 of the 3 pages
+    with pytest.raises(TraceB200Error):
+        eng.alloc_slot(128)                      # KV pool exhausted
+    eng.free_slot(a)
+    b = eng.alloc_slot(128)
+    eng.free_slot(b)
+    with pytest.raises(TraceB200Error):
+        eng.prefill([99], torch.zeros(1, 4, d.hidden, dtype=torch.float16, device="cuda"))   # unallocated slot
+    eng.close()
+    e2 = Engine(d, device=0, vit_chunk_frames=4, max_prefill_tokens=256, max_ctx=128)
+    with pytest.raises(TraceB200Error):          # weights missing: finalize must name the first missing tensor
+        e2.load_state_dict([])
+    e2.close()
