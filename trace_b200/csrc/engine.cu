@@ -64,6 +64,7 @@ struct trace_b200_ctx {
   // ViT workspaces (one chunk)
   __half *v_col = nullptr, *v_patch = nullptr, *v_h = nullptr, *v_y = nullptr, *v_qkv = nullptr, *v_attn = nullptr,
          *v_mlp = nullptr, *v_res = nullptr;
+  float* pj_scratch = nullptr;    // slot pool: logits + LN statistics per (frame, patch)
   // prefill workspaces
   __half *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_attn = nullptr, *p_act = nullptr;
   // decode workspaces + state
@@ -207,7 +208,8 @@ int allocate_all(trace_b200_ctx* ctx) {
   const size_t Fc = c.vit_chunk_frames;
   if (dalloc(ctx, &ctx->v_col, Fc * P * ctx->Kp) || dalloc(ctx, &ctx->v_patch, Fc * P * D) || dalloc(ctx, &ctx->v_h, Fc * NT * D) ||
       dalloc(ctx, &ctx->v_y, Fc * NT * D) || dalloc(ctx, &ctx->v_qkv, Fc * NT * 3 * D) || dalloc(ctx, &ctx->v_attn, Fc * NT * D) ||
-      dalloc(ctx, &ctx->v_mlp, Fc * NT * c.vit_mlp) || dalloc(ctx, &ctx->v_res, Fc * 8 * D))
+      dalloc(ctx, &ctx->v_mlp, Fc * NT * c.vit_mlp) || dalloc(ctx, &ctx->v_res, Fc * 8 * D) ||
+      dalloc(ctx, &ctx->pj_scratch, static_cast<size_t>(slot_pool_scratch_floats(static_cast<int>(Fc), static_cast<int>(P)))))
     return 1;
   const size_t Mp = c.max_prefill_tokens;
   if (dalloc(ctx, &ctx->p_h, Mp * H) || dalloc(ctx, &ctx->p_y, Mp * H) || dalloc(ctx, &ctx->p_qkv, Mp * ctx->qkvw) ||
@@ -406,7 +408,7 @@ int vit_chunk(trace_b200_ctx* ctx, const __half* pixels, int F, __half* res_out,
                               static_cast<size_t>(P) * D * 2, F, cudaMemcpyDeviceToDevice, s));
   }
   RUN(slot_pool_fused(ctx->v_h, D, NT, 1, P, D, F, ctx->pj_ln_w, ctx->pj_ln_b, 1e-6f, ctx->pj_slots, ctx->pj_cos,
-                      ctx->pj_sin, ctx->v_res, s));
+                      ctx->pj_sin, ctx->pj_scratch, ctx->v_res, s));
   RUN(gemm_f16(ctx->v_res, D, ctx->pj_readout, D, res_out, c.hidden, F * 8, c.hidden, D, nullptr, nullptr, 0, 0, 0, sms, s));
   return 0;
 }

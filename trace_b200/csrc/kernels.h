@@ -42,7 +42,9 @@ int attention_tc_fwd(const __half* qkv, int width, __half* O, int seqlen, int o_
 // feats: rows of width D with pitch ld; frame f owns rows [f*frame_rows + row_off, +n).  res [F*8, D] fp16.
 int slot_pool_fused(const __half* feats, int ld, int frame_rows, int row_off, int n, int D, int F,
                     const __half* ln_w, const __half* ln_b, float eps, const __half* slots /*[D,8]*/,
-                    const float* cos_tab, const float* sin_tab /*[n, D/2]*/, __half* res, cudaStream_t stream);
+                    const float* cos_tab, const float* sin_tab /*[n, D/2]*/, float* scratch /*slot_pool_scratch_floats(F, n)*/,
+                    __half* res, cudaStream_t stream);
+int slot_pool_scratch_floats(int F, int n);
 
 // ---- splice.cu : prefill activation assembly (prompt splice + time rows) -------------------------------------
 int splice_prefill(const int64_t* ids /*[B,L]*/, int B, int L, int T, const __half* slots /*[B*T*8,H]*/,
