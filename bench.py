@@ -38,8 +38,8 @@ TOKENS_PER_EVENT = 40     # synth.TOKENS_PER_EVENT: 13 time + 4 score + 22 capti
 L_TEXT = 224              # fixed prompt length
 MAX_NEW = 512             # evaluate.py:449
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_step_kernel launch (ncu, B=1, context ~2020), see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = 14248.98e6 + 115.95e6
-NCU_DRAM_SOURCE = "profiles/r01_ncu_full_decode_step_session2.csv (ncu --set full, one decode_step_kernel<1> launch, context 2017)"
+NCU_DRAM_BYTES_PER_LAUNCH = 14245.12e6 + 118.06e6
+NCU_DRAM_SOURCE = "profiles/r01_ncu_full_decode_step_final.csv (ncu --set full, one decode_step_kernel<1> launch, context 2017)"
 
 
 def parse_args():

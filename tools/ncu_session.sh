@@ -7,4 +7,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1; echo "launch list exit $?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:decode_step -s 2 -c 1 -f -o gpurun_out/prof_decode $CMD > gpurun_out/ncu_decode.log 2>&1; echo "decode full exit $?"
 timeout 400 ncu --set full --clock-control none -k regex:gemm_tc -s 60 -c 6 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1; echo "gemm full exit $?"
+timeout 300 ncu --set full --clock-control none -k regex:attn_tc -s 10 -c 2 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1; echo "attn full exit $?"
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv
