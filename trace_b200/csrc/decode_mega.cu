@@ -431,6 +431,28 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
   const float scale = rsqrtf(static_cast<float>(MG_HD));
   const float* cs = ctl.cs;
   const float* sn = ctl.sn;
+  // The cached K/V rows of the first pass do not depend on this step's q/k/v: request them BEFORE the q load + RoPE, so the
+  // two memory round trips of the phase overlap instead of following each other.
+  const int start = ctl.start;
+  const int nloc = max(ctl.end - start, 0);
+  const int hf = lane & 1;
+  uint4 kreg[8];
+  uint2 vreg[16];
+  auto load_kv = [&](int base) {
+    // K half row of key (warp*16 + lane/2), V 4-dim slices of the warp's 16 keys
+    const int jk = base + warp * 16 + (lane >> 1);
+    const int key = start + (jk < nloc ? jk : 0);
+    const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = base + warp * 16 + u;
+      const int keyv = start + (j < nloc ? j : 0);
+      vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
+    }
+  };
+  load_kv(0);
   for (int i = tid; i < MG_G * (MG_HD / 2); i += GV_CONS) {
     const int h = i / (MG_HD / 2), d = i % (MG_HD / 2);
     const __half* qp = row + (kv * MG_G + h) * MG_HD;
@@ -460,31 +482,14 @@ __device__ __forceinline__ void attn_item(const MegaParams& p, const MegaLayer& 
       vnew[d + 1] = f.y;
     }
   }
-  const int start = ctl.start;
-  const int nloc = max(ctl.end - start, 0);
   float m_w[MG_G], l_w[MG_G], o_w[MG_G][4];
 #pragma unroll
   for (int h = 0; h < MG_G; ++h) { m_w[h] = -INFINITY; l_w[h] = 0.f; o_w[h][0] = o_w[h][1] = o_w[h][2] = o_w[h][3] = 0.f; }
-  const int hf = lane & 1;
   bool first = true;
   for (int base = 0; base < nloc || first; base += GV_WARPS * 16) {
-    // ---- request this pass's rows: K half row of key (warp*16 + lane/2), V 4-dim slices of the warp's 16 keys ----
     const int jk = base + warp * 16 + (lane >> 1);
     const bool kvalid = jk < nloc;
-    uint4 kreg[8];
-    uint2 vreg[16];
-    {
-      const int key = start + (kvalid ? jk : 0);
-      const __half* kr = L.k_pool + ((static_cast<size_t>(ctl.pages[key / page_size - pg0]) * kvh + kv) * page_size + key % page_size) * MG_HD + hf * 64;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kreg[c] = *reinterpret_cast<const uint4*>(kr + c * 8);
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int j = base + warp * 16 + u;
-        const int keyv = start + (j < nloc ? j : 0);
-        vreg[u] = *reinterpret_cast<const uint2*>(L.v_pool + ((static_cast<size_t>(ctl.pages[keyv / page_size - pg0]) * kvh + kv) * page_size + keyv % page_size) * MG_HD + lane * 4);
-      }
-    }
+    if (base > 0) load_kv(base);              // pass 0 was requested before the q load
     // the LAST pass's latency-critical requests are out: the producer may start the O weights.  (With several passes per
     // CTA -- batch 4..8: 500-1000 keys per work item -- opening the gate after the first pass put every later pass behind
     // the weight stream's 3 us queue: 5.5 us per pass instead of ~1.5.)
