@@ -164,3 +164,35 @@ def test_engine_errors_are_loud():
     with pytest.raises(TraceB200Error):          # weights missing: finalize must name the first missing tensor
         e2.load_state_dict([])
     e2.close()
+
+
+@pytest.mark.parametrize("use_heads", [True, False])
+def test_forward_full_sequence_logits(use_heads):
+    """model.forward (trace_mistral.py:114-264): fp32 logits for every position of the spliced prompt, masked by `heads`
+    (32027 wide) or text-only (32001 wide), against the oracle's head_logits at each position."""
+    from trace_b200.model import TraceMistralConfig, TraceMistralForCausalLM
+    d = synth.tiny_dims(4)
+    model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, keep_head_weights=True, vit_chunk_frames=8, max_prefill_tokens=2048, max_ctx=512)
+    model.load_state_dict(dict(synth.iter_state_dict(d, 4)))
+    o = orc.TraceOracle(d, synth.make_state_dict(d, 4))
+    px, ts = synth.synthetic_clip(d, 4, seed=31, duration_s=25.0)
+    prompt = _prompt(10, 21)
+    ids = torch.tensor([prompt, prompt], dtype=torch.int64, device="cuda")
+    heads = [1, 2] if use_heads else None
+    out = model.forward(ids, attention_mask=torch.ones_like(ids), images_or_videos=[px.cuda(), px.cuda()], modal_list=["video"] * 2,
+                        video_timestamps=[ts, ts], heads=heads)
+    logits = out.logits
+    e = o.splice(prompt, o.encode_clip(px.float(), ts))
+    h, _ = o.llm_forward(e, None)
+    S = e.shape[0]
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (2, S, d.total_vocab if use_heads else d.vocab + 1)
+    for b in range(2):
+        head = heads[b] if use_heads else None
+        for pos in (0, 3, S // 2, S - 1):
+            want = o.head_logits(h[pos], head)
+            got = logits[b, pos].cpu()
+            fin = torch.isfinite(want)
+            assert torch.equal(torch.isfinite(got), fin), f"-inf mask differs at row {b} pos {pos}"
+            assert float((got[fin] - want[fin]).abs().max()) < LOGIT_TOL, f"row {b} pos {pos}: {float((got[fin] - want[fin]).abs().max())}"
+    with pytest.raises(NotImplementedError):
+        model.forward(ids, labels=ids)

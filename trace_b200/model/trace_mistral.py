@@ -96,7 +96,13 @@ class _Inner:
 class TraceMistralForCausalLM:
     config_class = TraceMistralConfig
 
-    def __init__(self, config: TraceMistralConfig, device: int = 0, **engine_kw):
+    _FORWARD_WEIGHTS = ("model.norm.weight", "lm_head.weight", "sync_head.weight", "time_head.weight", "score_head.weight")
+
+    def __init__(self, config: TraceMistralConfig, device: int = 0, keep_head_weights: bool = False, **engine_kw):
+        """`keep_head_weights`: also keep fp16 copies of the final norm and the four head matrices (262 MB for the full model)
+        on the Python side, which `forward()` (full-sequence logits) needs; `generate()` never does."""
+        self.keep_head_weights = keep_head_weights
+        self._fw = {}
         self.config = config
         self.dims = config.dims
         self.vocab_size = config.vocab_size
@@ -130,7 +136,73 @@ class TraceMistralForCausalLM:
         return self
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        self.engine.load_state_dict(state_dict.items() if hasattr(state_dict, "items") else state_dict)
+        items = list(state_dict.items() if hasattr(state_dict, "items") else state_dict)
+        if self.keep_head_weights:
+            for name, t in items:
+                if name in self._FORWARD_WEIGHTS:
+                    self._fw[name] = t.to(self.device, torch.float16).contiguous()
+        self.engine.load_state_dict(items)
+
+    # ---- forward (trace_mistral.py:114-264): full-sequence logits, prefill only ---------------------
+    @torch.no_grad()
+    def forward(self, input_ids: Optional[torch.Tensor] = None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                images_or_videos=None, return_dict=None, heads=None, video_timestamps=None, modal_list=None, **kwargs):
+        """logits for EVERY position of the (spliced) prompt, fp32 [B, S, 32027] with everything outside `heads[b]`'s range
+        set to -inf, or [B, S, 32001] when `heads` is None (trace_mistral.py:190-200, 244-252).  Inference only: `labels`
+        (the training losses), `past_key_values` (HF drives incremental decoding through `generate`, which runs on the
+        device-resident loop here) and `inputs_embeds` are rejected."""
+        if labels is not None or past_key_values is not None or inputs_embeds is not None:
+            raise NotImplementedError("trace_b200.forward covers the inference prefill (input_ids [+ images_or_videos]) only")
+        if not self._fw:
+            raise TraceB200Error("forward() needs keep_head_weights=True at construction (generate() does not)")
+        assert input_ids is not None and input_ids.dim() == 2
+        B, L = input_ids.shape
+        if heads is not None:
+            assert len(heads) == B                                                               # trace_mistral.py:245
+        ids = input_ids.to(self.device, torch.int64).contiguous()
+        if images_or_videos is None:
+            embeds = self.engine.build_prefill(ids, None, None)
+        else:
+            modal_list = modal_list or ["video"] * B
+            nf = self.num_frames()
+            clips = [x.unsqueeze(0).expand(nf, -1, -1, -1) if m == "image" else x for x, m in zip(images_or_videos, modal_list)]
+            T = clips[0].shape[0]
+            tid = torch.tensor([frame_time_ids(ts) for ts in video_timestamps], dtype=torch.int32, device=self.device)
+            embeds = self.engine.build_prefill(ids, self._encode_slots(clips), tid)
+        S = embeds.shape[1]
+        from ..engine import op_gemm, op_rmsnorm
+        d = self.dims
+        V = d.vocab
+        # the four heads stacked like the engine's own head matrix: row index = global token id (lm_head | sync | time | score)
+        w = torch.cat([self._fw["lm_head.weight"], self._fw["sync_head.weight"], self._fw["time_head.weight"],
+                       self._fw["score_head.weight"]], 0)
+        pad = (-w.shape[0]) % 256                                                                # whole GEMM tiles
+        if pad:
+            w = torch.cat([w, torch.zeros(pad, w.shape[1], dtype=w.dtype, device=w.device)], 0)
+        out = torch.empty((B, S, V + 27 if heads is not None else V + 1), dtype=torch.float32, device=self.device)
+        for b in range(B):
+            kv = self.engine.alloc_slot(S)
+            try:
+                hid = self.engine.prefill([kv], embeds[b:b + 1].contiguous(), return_hidden=True)
+            finally:
+                self.engine.free_slot(kv)
+            hn = op_rmsnorm(hid[0].contiguous(), self._fw["model.norm.weight"], d.rms_eps)
+            z = op_gemm(hn, w)[:, : V + 27].float()                                              # fp16 GEMM -> .float() (:191-200)
+            if heads is None:
+                out[b] = z[:, : V + 1]
+            else:
+                lo, hi = [(0, V + 1), (V + 1, V + 14), (V + 14, V + 27)][int(heads[b])]
+                z[:, :lo] = float("-inf")
+                z[:, hi:] = float("-inf")
+                out[b] = z
+        try:
+            from transformers.modeling_outputs import CausalLMOutputWithPast
+            return CausalLMOutputWithPast(loss=None, logits=out, past_key_values=None, hidden_states=None, attentions=None)
+        except Exception:  # noqa: BLE001
+            return types.SimpleNamespace(loss=None, logits=out, past_key_values=None, hidden_states=None, attentions=None)
+
+    __call__ = forward
 
     # ---- encode_images_or_videos (trace_arch.py:218-266) ------------------------------------------
     def _encode_slots(self, clips: List[torch.Tensor]) -> torch.Tensor:
