@@ -84,3 +84,57 @@ def test_surface_equals_reference_functions():
     assert r.constants.MMODAL_TOKEN_INDEX == __import__("trace_b200.constants", fromlist=["x"]).MMODAL_TOKEN_INDEX
     assert open("/root/reference/trace/prompts/dvc.txt").read() == prompts.DVC
     assert open("/root/reference/trace/prompts/mr.txt").read() == prompts.MR
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_number_tokenizers_equal_reference_towers():
+    """TimeTower.encode / ScoreTower.encode (time_encoder.py:52-68, score_encoder.py:52-68): '0>6.1f' / '0>3.1f' formatting
+    of the BINARY float (Python's correctly-rounded decimal), <sep> between numbers, trailing <sync>; and decode(id)."""
+    from oracle.ref_shim import load_reference
+    from trace_b200.model.encoders import ScoreTokenizer, TimeTokenizer, frame_time_ids
+    r = load_reference()
+    rt = r.TimeTower(r.TimeTokenizer(), hidden_dim=8)
+    rs = r.ScoreTower(r.ScoreTokenizer(), hidden_dim=8)
+    mt, ms = TimeTokenizer(), ScoreTokenizer()
+    rng = np.random.default_rng(3)
+    cases = [[0.0], [0.05], [0.15, 0.25], [9.95, 10.05], [99.95], [999.949999], [9999.9], [12.3, 456.7], [1e-9, 5.5]]
+    cases += [list(np.round(rng.uniform(0, 9999, rng.integers(1, 4)), rng.integers(0, 4))) for _ in range(200)]
+    for ts in cases:
+        ts = [float(x) for x in ts]
+        assert mt.encode_numbers(ts) == rt.encode(ts).tolist(), ts
+    for sc in [[0.0], [4.5], [9.95], [0.25, 3.75]] + [list(np.round(rng.uniform(0, 9.9, 1), 2)) for _ in range(50)]:
+        sc = [float(x) for x in sc]
+        assert ms.encode_numbers(sc) == rs.encode(sc).tolist(), sc
+    for i in range(13):
+        assert mt.decode(i) == rt.tokenizer.decode(i) and ms.decode(i) == rs.tokenizer.decode(i)
+    # per-frame rows: 6 ids, trailing <sync> dropped (trace_arch.py:243); 7 symbols (t >= 10000) trip the assert (:285)
+    assert frame_time_ids([[1.5], [20.25]]) == [rt.encode([1.5]).tolist()[:-1], rt.encode([20.25]).tolist()[:-1]]
+    with pytest.raises(AssertionError):
+        frame_time_ids([[1.0], [10000.0]])
+
+
+def test_expand2square_and_stopping_criteria():
+    from PIL import Image
+    from trace_b200.mm_utils import KeywordsStoppingCriteria, expand2square
+    import torch
+    im = Image.fromarray(np.full((4, 10, 3), 200, dtype=np.uint8))
+    sq = expand2square(im, (122, 116, 104))
+    a = np.asarray(sq)
+    assert a.shape == (10, 10, 3) and (a[3:7] == 200).all() and (a[:3] == [122, 116, 104]).all() and (a[7:] == [122, 116, 104]).all()
+    assert expand2square(sq, (0, 0, 0)) is sq
+    tk = synth.StandInTokenizer()
+    ids = torch.tensor([tk("hello world").input_ids])
+    crit = KeywordsStoppingCriteria(["</s>"], tk, ids)
+    assert crit.start_len == ids.shape[1] and crit(ids) in (True, False)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_expand2square_equals_reference():
+    from PIL import Image
+    from oracle.ref_shim import load_reference
+    from trace_b200.mm_utils import expand2square
+    r = load_reference()
+    rng = np.random.default_rng(1)
+    for h, w in ((5, 9), (9, 5), (7, 7), (6, 11)):
+        im = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        assert np.array_equal(np.asarray(expand2square(im, (122, 116, 104))), np.asarray(r.mm_utils.expand2square(im, (122, 116, 104))))
