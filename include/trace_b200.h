@@ -102,8 +102,8 @@ int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);
 /* device time (CUDA events on the engine's decode stream) and decoder passes of the last trace_b200_decode */
 int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps_out);
 
-/* debugging aid: %globaltimer stamps of the last fused decode step, [2 CTAs][layers][10 phase points] (needs
- * TRACE_B200_MEGA_TIMING=1 in the environment when the context is created). */
+/* debugging aid: %globaltimer stamps (and a few counters) of the last fused decode step, [2 CTAs][layers][32 slots]
+ * (needs TRACE_B200_MEGA_TIMING=1 in the environment when the context is created; tools/profile_step.py decodes it). */
 int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity);
 
 /* Frame pre-processing on the device: what process_video does per decoded frame on the host (trace/mm_utils.py:424-462):

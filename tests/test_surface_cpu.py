@@ -138,3 +138,60 @@ def test_expand2square_equals_reference():
     for h, w in ((5, 9), (9, 5), (7, 7), (6, 11)):
         im = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
         assert np.array_equal(np.asarray(expand2square(im, (122, 116, 104))), np.asarray(r.mm_utils.expand2square(im, (122, 116, 104))))
+
+
+def _write_video(path, n=30, fps=10.0, size=(64, 48)):
+    import cv2
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), fps, size)
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8)
+    for i in range(n):
+        w.write(np.roll(base, i, axis=1))
+    w.release()
+
+
+def test_process_video_host_path(tmp_path):
+    """process_video (mm_utils.py:379-471) on a generated clip: uniform sampler, [[idx/fps]] timestamps, pad-to-square with
+    the CLIP mean colour, CLIP preprocessing -> [T,3,S,S] fp32; and the >9999 s guard (:466-469)."""
+    import torch
+    from trace_b200.mm_utils import process_video
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    path = str(tmp_path / "clip.avi")
+    _write_video(path, n=30, fps=10.0)
+    proc = _ImageProcessor(56)
+    video, stamps = process_video(path, proc, aspect_ratio="pad", num_frames=4)
+    assert tuple(video.shape) == (4, 3, 56, 56) and video.dtype == torch.float32
+    assert stamps == [[0.0], [0.9], [1.9], [2.9]]                       # np.linspace(0, 29, 4, dtype=int) / fps
+    # top / bottom bands of the padded square are the mean colour -> ~0 after normalisation (int(mean*255)/255 - mean)
+    assert float(video[:, :, :3, :].abs().max()) < 0.02
+    _write_video(path, n=10002, fps=1.0, size=(16, 16))                 # last sampled frame at 10001 s > 9999
+    with pytest.raises(ImportError):
+        process_video(path, proc, aspect_ratio="pad", num_frames=4)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_config1_preprocessing_on_the_reference_asset():
+    """BASELINE config 1 plumbing: assets/sora.mp4, 8 frames -- our CLIP preprocessing equals the HF PIL processor the
+    reference uses (transformers 4.40.1 semantics) on the same decoded, padded frames."""
+    import cv2
+    import transformers
+    from PIL import Image
+    from trace_b200.mm_utils import expand2square, process_video
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    path = "/root/reference/assets/sora.mp4"
+    proc = _ImageProcessor(336)
+    video, stamps = process_video(path, proc, aspect_ratio="pad", num_frames=8)
+    assert tuple(video.shape) == (8, 3, 336, 336) and len(stamps) == 8 and stamps[0] == [0.0]
+    cap = cv2.VideoCapture(path)
+    n, fps = int(cap.get(cv2.CAP_PROP_FRAME_COUNT)), float(cap.get(cv2.CAP_PROP_FPS))
+    ids = np.linspace(0, n - 1, 8, dtype=int)
+    assert [s[0] for s in stamps] == [int(i) / fps for i in ids]
+    cls = getattr(transformers, "CLIPImageProcessorPil", None) or transformers.CLIPImageProcessor
+    hf = cls(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336})
+    for k in (0, 7):
+        cap.set(cv2.CAP_PROP_POS_FRAMES, int(ids[k]))
+        ok, bgr = cap.read()
+        assert ok
+        im = expand2square(Image.fromarray(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)), tuple(int(x * 255) for x in hf.image_mean))
+        want = hf.preprocess([im], return_tensors="np")["pixel_values"][0]
+        assert float(np.abs(video[k].numpy() - want).max()) < 1e-5
