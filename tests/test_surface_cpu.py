@@ -195,3 +195,59 @@ def test_config1_preprocessing_on_the_reference_asset():
         im = expand2square(Image.fromarray(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)), tuple(int(x * 255) for x in hf.image_mean))
         want = hf.preprocess([im], return_tensors="np")["pixel_values"][0]
         assert float(np.abs(video[k].numpy() - want).max()) < 1e-5
+
+
+def test_load_pretrained_model_safetensors_branch(tmp_path, monkeypatch):
+    """load_pretrained_model (model/builder.py:29-156, fp16 branch): config.json -> dims, every tensor of every *.safetensors
+    shard handed to the engine under its HF name as fp16, finalize, processor / context_len conventions.  The CUDA engine is
+    replaced by a recorder (host logic only)."""
+    import json
+    import torch
+    from safetensors.torch import save_file
+    from trace_b200.model import builder
+
+    d = synth.tiny_dims(4)
+    sd = {k: v.float() for k, v in synth.make_state_dict(d, 0).items()}     # fp32 on disk: the loader must cast to fp16
+    names = sorted(sd)
+    save_file({k: sd[k].contiguous() for k in names[: len(names) // 2]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k].contiguous() for k in names[len(names) // 2:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    cfg = {"hidden_size": d.hidden, "num_hidden_layers": d.layers, "num_attention_heads": d.heads, "num_key_value_heads": d.kv_heads,
+           "intermediate_size": d.ffn, "vocab_size": d.vocab, "rope_theta": 1e6, "rms_norm_eps": 1e-5, "num_frames": 4,
+           "mm_projector_type": "spatial_slot", "max_sequence_length": 4096,
+           "vision_config": {"hidden_size": d.vit_width, "num_attention_heads": d.vit_heads, "num_hidden_layers": d.vit_layers,
+                             "intermediate_size": d.vit_mlp, "image_size": d.image_size, "patch_size": d.patch_size}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+
+    class FakeEngine:
+        def __init__(self):
+            self.loaded, self.finalized = {}, False
+
+        def load_weight(self, name, t):
+            assert t.dtype == torch.float16
+            self.loaded[name] = t
+
+        def load_state_dict(self, items):
+            assert list(items) == []
+            self.finalized = True
+
+    class FakeModel:
+        def __init__(self, config, device=0, **kw):
+            self.config, self.engine, self.kw = config, FakeEngine(), kw
+
+        def get_vision_tower(self):
+            import types
+            return types.SimpleNamespace(image_processor="processor")
+
+    monkeypatch.setattr(builder, "TraceMistralForCausalLM", FakeModel)
+    tok, model, proc, ctx_len = builder.load_pretrained_model(str(tmp_path), None, "trace", device="cuda")
+    assert model.engine.finalized and sorted(model.engine.loaded) == names
+    for k in names[:: max(1, len(names) // 7)]:
+        assert torch.equal(model.engine.loaded[k], sd[k].half())
+    got = model.config.dims
+    assert (got.hidden, got.layers, got.ffn, got.vit_width, got.image_size, got.num_frames) == (d.hidden, d.layers, d.ffn, d.vit_width, d.image_size, 4)
+    assert proc == "processor" and ctx_len == 4096 and model.config.mm_projector_type == "spatial_slot"
+    assert tok.bos_token_id == 1 and tok.eos_token_id == 2            # weight-only export -> stand-in tokenizer
+    with pytest.raises(NotImplementedError):
+        builder.load_pretrained_model(str(tmp_path), None, "trace-lora")
+    with pytest.raises(NotImplementedError):
+        builder.load_pretrained_model(str(tmp_path), None, "trace", load_4bit=True)

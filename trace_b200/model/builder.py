@@ -18,7 +18,13 @@ from .trace_mistral import TraceMistralConfig, TraceMistralForCausalLM
 
 
 def _dims_from_hf_config(cfg: dict) -> synth.TraceDims:
+    """Mistral keys from config.json; the CLIP tower's geometry is not stored there in the reference (it loads
+    `mm_vision_tower` by name, trace_arch.py:34-36) -- an optional `vision_config` block overrides the ViT-L/14-336 defaults."""
+    v = cfg.get("vision_config", {}) or {}
+    extra = {k2: v[k1] for k1, k2 in (("hidden_size", "vit_width"), ("num_attention_heads", "vit_heads"), ("num_hidden_layers", "vit_layers"),
+                                      ("intermediate_size", "vit_mlp"), ("image_size", "image_size"), ("patch_size", "patch_size")) if k1 in v}
     return synth.TraceDims(
+        **extra,
         hidden=cfg.get("hidden_size", 4096), layers=cfg.get("num_hidden_layers", 32), heads=cfg.get("num_attention_heads", 32),
         kv_heads=cfg.get("num_key_value_heads", 8), head_dim=cfg.get("head_dim", 128), ffn=cfg.get("intermediate_size", 14336),
         vocab=cfg.get("vocab_size", 32000), rope_theta=float(cfg.get("rope_theta", 1e6)), rms_eps=float(cfg.get("rms_norm_eps", 1e-5)),
@@ -43,7 +49,7 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     else:
         cfg = json.load(open(os.path.join(model_path, "config.json")))
         d = _dims_from_hf_config(cfg)
-        model = TraceMistralForCausalLM(TraceMistralConfig(d, **{k: v for k, v in cfg.items() if k.startswith("mm_")}), device=dev, **kwargs)
+        model = TraceMistralForCausalLM(TraceMistralConfig(d, **{k: v for k, v in cfg.items() if k not in ("vision_config", "architectures")}), device=dev, **kwargs)
         shards = sorted(glob.glob(os.path.join(model_path, "*.safetensors"))) or sorted(glob.glob(os.path.join(model_path, "pytorch_model*.bin")))
         if not shards:
             raise FileNotFoundError(f"no weight shards under {model_path}")
@@ -56,8 +62,11 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
             for name, t in part.items():
                 model.engine.load_weight(name, t.half())
         model.engine.load_state_dict([])
-        from transformers import AutoTokenizer
-        tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
+        if any(os.path.exists(os.path.join(model_path, f)) for f in ("tokenizer.model", "tokenizer.json", "tokenizer_config.json")):
+            from transformers import AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)                # builder.py:113
+        else:   # weight-only export (offline tests): the deterministic stand-in used by the bench
+            tokenizer = synth.StandInTokenizer(d.vocab)
     processor = model.get_vision_tower().image_processor                       # builder.py:149
     context_len = getattr(model.config, "max_sequence_length", 2048)            # builder.py:151-154
     return tokenizer, model, processor, context_len
