@@ -151,7 +151,9 @@ class TraceMistralForCausalLM:
         """logits for EVERY position of the (spliced) prompt, fp32 [B, S, 32027] with everything outside `heads[b]`'s range
         set to -inf, or [B, S, 32001] when `heads` is None (trace_mistral.py:190-200, 244-252).  Inference only: `labels`
         (the training losses), `past_key_values` (HF drives incremental decoding through `generate`, which runs on the
-        device-resident loop here) and `inputs_embeds` are rejected."""
+        device-resident loop here) and `inputs_embeds` are rejected.  Without `images_or_videos` the ids are embedded as
+        generate's text-only branch does (`embed_tokens(inputs)`, :306-307); the reference's own forward cannot take
+        multi-token `input_ids` without images (trace_arch.py:359 applies Python `and` to tensors)."""
         if labels is not None or past_key_values is not None or inputs_embeds is not None:
             raise NotImplementedError("trace_b200.forward covers the inference prefill (input_ids [+ images_or_videos]) only")
         if not self._fw:
