@@ -347,7 +347,6 @@ struct MegaParams {
   int kp_qkv, ks_qkv, kp_o, ks_o, kp_gu, ks_gu, kp_dn, ks_dn, kp_hd, ks_hd;
   unsigned long long* dbg;            // optional timeline [2 CTAs][layers][10] of %globaltimer stamps
   int pf_ahead;                       // (experimental, off) TMA L2 prefetch distance of the weight stream, in stages
-  int pf_gap_kb, pf_attn_kb;          // consumer-issued L2 prefetch of the next phase's rows during barrier / attention gaps
   int part_bytes, stages, xs_cap;      // xs_cap: halves per batch row reserved for staged activations (max KP + pad)
   int relay_sites;                    // bit t: the barrier before phase type t parks stages (bit 5: the one before attention)
   int early_release;                  // hand a ring stage back before (1) or after (0) its MMA chain
@@ -716,23 +715,6 @@ __device__ __forceinline__ void attn_prefetch(const MegaParams& p, const MegaLay
   }
 }
 
-// While the consumer warps are about to idle in a grid barrier (or in the latency-bound attention phase) the HBM pipe
-// drains: the producer's shared-memory ring (4 x 33 KB) only covers ~3 us of streaming.  The consumers therefore ask L2
-// for the part of their NEXT weight rows that lies beyond the ring (this CTA's rows of a row-major matrix are one
-// contiguous byte range) with plain prefetch.global.L2 hints -- LSU work on otherwise idle threads, nothing added to the
-// TMA queue -- so that the ring refills from L2 instead of HBM when the phase starts.
-__device__ __forceinline__ void prefetch_next_rows(const __half* W, int K, int N, int skip_rows, int max_kb) {
-  if (max_kb <= 0) return;
-  int r0, r1;
-  cta_rows(N, r0, r1);
-  const long long avail = static_cast<long long>(r1 - r0 - skip_rows) * K * 2;
-  if (avail <= 0) return;
-  const long long bytes = avail < static_cast<long long>(max_kb) * 1024 ? avail : static_cast<long long>(max_kb) * 1024;
-  const char* base = reinterpret_cast<const char*>(W + static_cast<size_t>(r0 + skip_rows) * K);
-  for (long long off = static_cast<long long>(threadIdx.x) * 128; off < bytes; off += static_cast<long long>(GV_CONS) * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-}
-
 // Phase geometry, indexed by phase type (0 qkv, 1 o, 2 gate/up, 3 down, 4 head).  The kernel body is ONE loop over the
 // 4*layers+1 phases of the step with one copy of every building block: the step's code (~350 KB of SASS when every
 // phase had its own inlined copy) is re-executed for each of the 32 layers, and anything that does not fit the
@@ -1065,7 +1047,7 @@ int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream) {
   p.part_o = a.part_o; p.part_ml = a.part_ml; p.counters = a.counters; p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
   p.logits_out = a.logits_out; p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
   p.eos = a.eos; p.pad = a.pad; p.st = a.st; p.gbar = a.gbar; p.gexit = a.gbar + 1;
-  p.pf_ahead = a.pf_ahead; p.pf_gap_kb = a.pf_gap_kb; p.pf_attn_kb = a.pf_attn_kb;
+  p.pf_ahead = a.pf_ahead;
   p.tm_relay = a.tm_relay; p.gate_mode = a.gate_mode;
   p.max_inflight = a.max_inflight; p.early_release = a.early_release; p.relay_sites = a.relay_sites;
   p.dbg = a.dbg;

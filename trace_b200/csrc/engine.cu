@@ -92,7 +92,7 @@ struct trace_b200_ctx {
   unsigned* d_gbar = nullptr;
   unsigned long long* d_dbg = nullptr;
   bool fused_decode = true;
-  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, pf_gap_kb = 0, pf_attn_kb = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
+  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
   bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
 };
 
@@ -243,8 +243,6 @@ int allocate_all(trace_b200_ctx* ctx) {
     ctx->tm_relay = env_int("TRACE_B200_TM_RELAY", 0, 2, 0);
     ctx->gate_mode = env_int("TRACE_B200_GATE_MODE", 0, 2, ctx->tm_relay ? 2 : 1);
     ctx->pf_ahead = env_int("TRACE_B200_PF_AHEAD", 0, 64, 0);
-    ctx->pf_gap_kb = env_int("TRACE_B200_PF_GAP_KB", 0, 4096, 0);
-    ctx->pf_attn_kb = env_int("TRACE_B200_PF_ATTN_KB", 0, 4096, 0);
     ctx->max_inflight = env_int("TRACE_B200_INFLIGHT", 0, 3, 0);
     ctx->early_release = env_int("TRACE_B200_EARLY_REL", 0, 1, 1);
     ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 4);
@@ -459,7 +457,7 @@ int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out,
     a.part_ml = ctx->d_part_ml; a.counters = ctx->d_counters; a.cand_val = ctx->d_cand_val; a.cand_idx = ctx->d_cand_idx;
     a.logits_out = logits_out; a.embed = ctx->embed; a.time_tab = ctx->time_tab; a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab;
     a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar; a.dbg = ctx->d_dbg;
-    a.tm_relay = ctx->tm_relay; a.gate_mode = ctx->gate_mode; a.pf_ahead = ctx->pf_ahead; a.pf_gap_kb = ctx->pf_gap_kb; a.pf_attn_kb = ctx->pf_attn_kb; a.max_inflight = ctx->max_inflight; a.early_release = ctx->early_release; a.max_stages = ctx->max_stages; a.relay_sites = ctx->relay_sites;
+    a.tm_relay = ctx->tm_relay; a.gate_mode = ctx->gate_mode; a.pf_ahead = ctx->pf_ahead; a.max_inflight = ctx->max_inflight; a.early_release = ctx->early_release; a.max_stages = ctx->max_stages; a.relay_sites = ctx->relay_sites;
     RUN(decode_step_fused(a, s));
     return 0;
   }

@@ -123,7 +123,7 @@ struct DecodeMegaArgs {
   // tuning switches (engine.cu reads them from the environment when the context is created)
   int tm_relay;                  // TMEM weight reservoir: 0 off, 1 on (default), 2 test mode (park greedily at every barrier)
   int gate_mode;                 // producer waits for the attention K/V requests before 1: the O weights, 2: the gate/up weights, 0: never
-  int pf_ahead, pf_gap_kb, pf_attn_kb;   // experimental L2 prefetch distances (0 = off, the default)
+  int pf_ahead;                  // experimental TMA L2 prefetch distance of the weight stream in stages (0 = off, the default)
   int max_inflight;              // weight-stream request throttle in stages (0 = ring depth)
   int relay_sites;               // TMEM reservoir: which barriers park stages (bit = phase type that follows, bit 5 = before attention)
   int early_release, max_stages; // ring stage handed back before its MMA chain (default 1); cap on ring stages (0 = what fits)
