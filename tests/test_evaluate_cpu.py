@@ -1,0 +1,108 @@
+"""The evaluation driver (trace_b200/eval/evaluate.py, mirroring trace/eval/evaluate.py) end to end on CPU with generated
+videos and a recorder model: annotation loading, prompt construction, batching, event parsing, the result file the
+reformat scripts read."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from trace_b200 import synth
+from trace_b200.eval import evaluate as ev
+from trace_b200.eval import reformat_dvc
+
+
+def _write_video(path, n, fps=10.0, size=(64, 48)):
+    import cv2
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), fps, size)
+    for i in range(n):
+        w.write(np.full((size[1], size[0], 3), (i * 5) % 255, np.uint8))
+    w.release()
+
+
+V = 32000
+
+
+def _event_ids(k):
+    """time head: 0012.5<sep>0030.0<sync>  score head: 4.5<sync>  text head: two caption tokens <sync>"""
+    tb, sb = V + 1, V + 14
+    t = [tb + 2, tb + 2, tb + 3, tb + 4, tb + 12, tb + 7, tb + 1, tb + 2, tb + 2, tb + 5, tb + 2, tb + 12, tb + 2, tb]
+    s = [sb + 6, sb + 12, sb + 7, sb]
+    return t + s + [100 + k, 200 + k, V]
+
+
+class FakeModel:
+    vocab_size = V
+    device = torch.device("cpu")
+
+    def __init__(self):
+        import types
+        self.config = types.SimpleNamespace(image_aspect_ratio="pad")
+        self.generation_config = types.SimpleNamespace(eos_token_id=2, pad_token_id=None)
+        self.batches = []
+
+    def _encode_slots(self, clips):
+        return torch.stack([c.float().mean().reshape(1, 1, 1).expand(c.shape[0], 8, 4) for c in clips], 0)
+
+    def _generate_from_slots(self, ids, slots, tid, heads, max_new, eos, pad):
+        self.batches.append(ids.shape[0])
+        rows = []
+        for b in range(ids.shape[0]):
+            T = tid.shape[1]
+            if T == 4:    # "short" videos: two events, the second caption closed by EOS
+                row = _event_ids(1) + _event_ids(2)[:-1] + [eos]
+            else:         # output that ends exactly on a <sync>: printed but not saved
+                row = _event_ids(3)
+            rows.append(row)
+            heads[b] = 0
+        n = max(len(r) for r in rows)                      # max_new_tokens reached right after the <sync> for the T=8 rows
+        return torch.tensor([r + [pad] * (n - len(r)) for r in rows], dtype=torch.int64)
+
+
+def test_evaluate_driver_end_to_end(tmp_path, monkeypatch, capsys):
+    vids = tmp_path / "videos"
+    vids.mkdir()
+    anno = {"annotations": []}
+    for k in range(5):
+        _write_video(str(vids / f"v{k}.avi"), n=20 + k)
+        anno["annotations"].append({"image_id": f"some/dir/v{k}.avi", "id": 100 + k, "caption": f" query {k}. ", "duration": 3.0})
+    anno["annotations"].append({"image_id": "missing.avi", "id": 999, "caption": "x", "duration": 1.0})
+    (tmp_path / "val.caption_coco_format.json").write_text(json.dumps(anno))
+    (tmp_path / "prompt.txt").write_text("Find the moment described by: '{}'.\nsecond line is ignored\n")
+    fake = FakeModel()
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    tok = synth.StandInTokenizer()
+    monkeypatch.setattr(ev, "load_pretrained_model", lambda *a, **k: (tok, fake, _ImageProcessor(56), 2048))
+    args = ev.build_parser().parse_args(["--anno_path", str(tmp_path), "--video_path", str(vids), "--task", "tvg", "--dataset", "toy",
+                                         "--output_dir", str(tmp_path / "out"), "--split", "val", "--num_frames", "4", "--batch_size", "3",
+                                         "--max_new_tokens", "64", "--prompt_file", str(tmp_path / "prompt.txt"), "--model_path", "ckpt/toy"])
+    out_path, results = ev.main(args)
+    capsys.readouterr()
+    assert os.path.basename(out_path) == "fmt_toy_val_f4_result.json" and json.load(open(out_path)) == results
+    assert fake.batches == [3, 2]                       # 5 existing videos, --batch_size 3 (the reference would evaluate only 2 of them)
+    assert [r["id"] for r in results] == [100, 101, 102, 103, 104]
+    r0 = results[0]
+    assert r0["video"].endswith("v0.avi") and r0["timestamps"] == [[12.5, 30.0], [12.5, 30.0]] and r0["scores"] == [[4.5], [4.5]]
+    assert len(r0["captions"]) == 2
+    dvc = reformat_dvc(results)
+    assert dvc["v0.avi"][0]["timestamp"] == [12.5, 30.0]
+    # prompt: first line of the file only, formatted with the stripped query, llama_2 template, <video> sentinel, trailing <sync>
+    ids = ev.build_prompt_ids(ev.read_txt(str(tmp_path / "prompt.txt")).format("query 0."), tok)
+    assert ids[0] == 1 and int((ids == -201).sum()) == 1 and ids[-1] == -205
+
+
+def test_output_ending_on_sync_is_not_saved(tmp_path, monkeypatch, capsys):
+    vids = tmp_path / "videos"
+    vids.mkdir()
+    _write_video(str(vids / "a.avi"), n=30)
+    (tmp_path / "val.caption_coco_format.json").write_text(json.dumps({"annotations": [{"image_id": "a.avi", "id": 1, "caption": "c", "duration": 3.0}]}))
+    (tmp_path / "prompt.txt").write_text("Describe.\n")
+    fake = FakeModel()
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    monkeypatch.setattr(ev, "load_pretrained_model", lambda *a, **k: (synth.StandInTokenizer(), fake, _ImageProcessor(56), 2048))
+    args = ev.build_parser().parse_args(["--anno_path", str(tmp_path), "--video_path", str(vids), "--task", "dvc", "--dataset", "toy",
+                                         "--output_dir", str(tmp_path / "out"), "--num_frames", "8", "--batch_size", "1",
+                                         "--prompt_file", str(tmp_path / "prompt.txt"), "--model_path", "ckpt/toy"])
+    _, results = ev.main(args)
+    out = capsys.readouterr().out
+    assert results == [] and "'timestamps': [[12.5, 30.0]]" in out      # printed, not saved (evaluate.py:409-411)
