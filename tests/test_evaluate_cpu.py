@@ -106,3 +106,37 @@ def test_output_ending_on_sync_is_not_saved(tmp_path, monkeypatch, capsys):
     _, results = ev.main(args)
     out = capsys.readouterr().out
     assert results == [] and "'timestamps': [[12.5, 30.0]]" in out      # printed, not saved (evaluate.py:409-411)
+
+
+def test_inference_script_video_and_image(tmp_path, monkeypatch, capsys):
+    """scripts/inference flow (inference.py:15-128) with a recorder model: video and image inputs, prompt, parsed events."""
+    from PIL import Image
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    from trace_b200.scripts import inference as inf
+
+    class GenModel:
+        vocab_size = V
+
+        def __init__(self):
+            import types
+            self.config = types.SimpleNamespace(image_aspect_ratio="pad", num_frames=4)
+            self.calls = []
+
+        def generate(self, input_ids, **kw):
+            self.calls.append((tuple(input_ids.shape), kw["modal_list"], tuple(kw["images_or_videos"][0].shape), len(kw["video_timestamps"][0]),
+                               kw["heads"], kw["do_sample"], kw["max_new_tokens"]))
+            return torch.tensor([_event_ids(1) + [7, 8, 2]])
+
+    m = GenModel()
+    monkeypatch.setattr(inf, "load_pretrained_model", lambda *a, **k: (synth.StandInTokenizer(), m, _ImageProcessor(56), 2048))
+    vid = str(tmp_path / "c.avi")
+    _write_video(vid, n=24)
+    out = inf.main(["--model_path", "ckpt/toy", "--video", vid, "--num_frames", "6", "--max_new_tokens", "32"])
+    assert out["timestamps"] == [[12.5, 30.0]] and out["scores"] == [[4.5]] and len(out["captions"]) == 2
+    img = str(tmp_path / "i.png")
+    Image.fromarray(np.full((40, 70, 3), 90, np.uint8)).save(img)
+    inf.main(["--model_path", "ckpt/toy", "--image", img])
+    capsys.readouterr()
+    (s0, modal0, shape0, nts0, heads0, samp0, mx0), (s1, modal1, shape1, nts1, *_rest) = m.calls
+    assert modal0 == ["video"] and shape0 == (6, 3, 56, 56) and nts0 == 6 and heads0 == [1] and samp0 is False and mx0 == 32
+    assert modal1 == ["image"] and shape1 == (3, 56, 56) and nts1 == 4

@@ -1,4 +1,4 @@
-"""Pre-processing utilities of the TRACE surface (mirrors trace/mm_utils.py: process_video :379-471,
+"""Pre-processing utilities of the TRACE surface (mirrors trace/mm_utils.py: process_image :358-376, process_video :379-471,
 expand2square :259-270, tokenizer_MMODAL_token(_all) :496-554, get_model_name_from_path :558-564,
 KeywordsStoppingCriteria :567-600).  Host (CPU) work exactly as in the reference; frames are decoded with OpenCV
 because decord is not available offline."""
@@ -38,6 +38,18 @@ def _read_video(path: str):
     n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
     fps = float(cap.get(cv2.CAP_PROP_FPS))
     return cap, n, fps
+
+
+def process_image(image_path, processor, aspect_ratio="pad", num_frames=NUM_FRAMES, image_grid=False):
+    """path -> Tensor[1,3,H,W] fp32: RGB, pad to square with the CLIP mean colour, CLIP preprocessing (mm_utils.py:358-376).
+    The model repeats an `image` input `num_frames` times itself (trace_arch.py:221)."""
+    from PIL import Image
+    if image_grid:
+        raise NotImplementedError("image_grid is not used by the inference drivers")
+    image = Image.open(image_path).convert("RGB")
+    if aspect_ratio == "pad":
+        image = expand2square(image, tuple(int(x * 255) for x in processor.image_mean))
+    return processor.preprocess([image], return_tensors="pt")["pixel_values"]
 
 
 def process_video(video_path, processor, aspect_ratio="pad", num_frames=NUM_FRAMES, image_grid=False, sample_scheme="uniform",
