@@ -140,3 +140,75 @@ def test_inference_script_video_and_image(tmp_path, monkeypatch, capsys):
     (s0, modal0, shape0, nts0, heads0, samp0, mx0), (s1, modal1, shape1, nts1, *_rest) = m.calls
     assert modal0 == ["video"] and shape0 == (6, 3, 56, 56) and nts0 == 6 and heads0 == [1] and samp0 is False and mx0 == 32
     assert modal1 == ["image"] and shape1 == (3, 56, 56) and nts1 == 4
+
+
+def test_videomme_driver(tmp_path, monkeypatch, capsys):
+    """Video-MME MCQ flow (videomme/evaluate.py): segment-centre sampler, no-pad CLIP transform, option extraction, per-category
+    accuracy files; several questions about one video share a single clip encode (config 5: mixed 4 / 8 frame buckets)."""
+    from trace_b200.eval import videomme as vm
+    from trace_b200.model.trace_mistral import _ImageProcessor
+    idx, msg = vm.get_index(4, 10.0, 39)
+    assert idx.tolist() == [4, 14, 24, 33] and msg[1] == [1.4]                      # int(4.875 + np.round(9.75 * i)): 4, 14, 24 (19.5 -> 20), 33
+    q, a = vm.qa_template({"question": "What?", "options": ["A. cat", "B. dog", "C. emu", "D. fox"], "answer": "C"})
+    assert q == "Question: What?\nOptions:\n(A) cat\n(B) dog\n(C) emu\n(D) fox" and a == "(C) emu"
+    assert vm.extract_option("(B) dog") == "b" and vm.extract_option("Best option: c.") == "c"
+    (tmp_path / "data").mkdir()
+    for name, n in (("vidA", 40), ("vidB", 30)):
+        _write_video(str(tmp_path / "data" / f"{name}.mp4"), n=n)
+    anno = []
+    for k, (name, ans) in enumerate([("vidA", "A"), ("vidA", "B"), ("vidB", "A"), ("vidA", "C"), ("nope", "A")]):
+        anno.append({"url": f"https://www.youtube.com/watch?v={name}", "duration": "short" if name == "vidA" else "long",
+                     "question": f"q{k}", "options": ["A. a", "B. b", "C. c", "D. d"], "answer": ans})
+    (tmp_path / "test.json").write_text(json.dumps(anno))
+
+    class McqModel(FakeModel):
+        def _generate_from_slots(self, ids, slots, tid, heads, max_new, eos, pad):
+            self.batches.append(ids.shape[0])
+            assert max_new == 128
+            tb = V + 1
+            # timestamps "0001.0<sync>", score "1.0<sync>", caption tokens spelling "( a )" in the stand-in vocabulary, EOS
+            row = [tb + 2, tb + 2, tb + 2, tb + 3, tb + 12, tb + 2, tb] + [V + 14 + 3, V + 14 + 12, V + 14 + 2, V + 14] + [300, eos]
+            return torch.tensor([row] * ids.shape[0], dtype=torch.int64)
+
+    fake = McqModel()
+    tok = synth.StandInTokenizer()
+    monkeypatch.setattr(tok, "decode", lambda toks, **k: "(A) a", raising=False)
+    monkeypatch.setattr(vm, "load_pretrained_model", lambda *a, **k: (tok, fake, _ImageProcessor(56), 2048))
+    args = vm.build_parser().parse_args(["--anno_path", str(tmp_path / "test.json"), "--data_dir", str(tmp_path), "--output_dir",
+                                         str(tmp_path / "out"), "--num_frames", "4", "--model_path", "ckpt/toy"])
+    acc, res, stats = vm.main(args)
+    capsys.readouterr()
+    assert acc == {"short": [1, 3], "long": [1, 1]}                                  # every prediction is "a"
+    assert stats["clips_encoded"] == 2 and stats["clip_encodes_saved"] == 2          # vidA encoded once for its 3 questions
+    board = json.load(open(tmp_path / "out" / "upload_leaderboard.json"))
+    assert abs(board["short"] - 100 / 3) < 1e-9 and board["long"] == 100.0 and board["Avg"] == 50.0
+    assert json.load(open(tmp_path / "out" / "test.json"))["res_list"][0] == {"pred": ["a"], "gt": ["a"]}
+
+
+def test_videomme_helpers_equal_reference_source():
+    """get_index / qa_template executed from the reference's own source text (the module itself needs decord / accelerate)."""
+    import ast
+    import types
+    import pytest
+    ref = "/root/reference/trace/eval/videomme/evaluate.py"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference not mounted (GPU box)")
+    from trace_b200.eval import videomme as vm
+    src = open(ref).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MME_dataset")
+    ns = {"np": np}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("get_index", "qa_template"):
+            exec(compile(ast.Module(body=[fn], type_ignores=[]), ref, "exec"), ns)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        T = int(rng.integers(1, 130))
+        fps = float(rng.uniform(5, 60))
+        max_frame = int(rng.integers(T, 100000))
+        me = types.SimpleNamespace(num_segments=T)
+        want_idx, want_msg = ns["get_index"](me, None, fps, max_frame, first_idx=0)
+        got_idx, got_msg = vm.get_index(T, fps, max_frame)
+        assert got_idx.tolist() == want_idx.tolist() and got_msg == want_msg
+    d = {"question": "Why?", "options": ["A. one", "B. two words", "C. 3", "D. four"], "answer": "B"}
+    assert vm.qa_template(d) == ns["qa_template"](None, d)
