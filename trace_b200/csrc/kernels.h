@@ -26,7 +26,7 @@ int vit_im2col(const __half* pixels, __half* out, int F, int image, int ps, int 
 int vit_embed_ln(const __half* patch, const __half* cls, const __half* pos, const __half* ln_w, const __half* ln_b,
                  float eps, __half* out, int F, int P, int D, cudaStream_t stream);
 
-// ---- attention.cu : flash-style attention on mma.sync (legacy tensor path; tcgen05 version is round-2 work) ----
+// ---- attention.cu : flash-style attention on mma.sync (legacy tensor path, TRACE_B200_ATTN_TC=0; the default is attention_tc.cu) ----
 // Q/K/V element pointers with row strides (elements) and per-batch strides; head h uses columns [h*HD, (h+1)*HD)
 // of Q/O and [(h/group)*HD, ...) of K/V.  HD in {64, 128}.
 int attention_fwd(const __half* Q, const __half* K, const __half* V, __half* O, int seqlen, int q_stride,
