@@ -96,6 +96,25 @@ int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, co
 int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new,
                       int eos, int pad, int64_t* ids_out_host, int* n_out, float* logits_out_dev, void* stream);
 
+/* Sampling of the following trace_b200_decode calls: HF GenerationMixin._sample with the default logits warpers as
+ * scripts/inference/inference.py:62,71-73 drives it (do_sample=True, temperature=0.2; generation_config top_k=50, top_p=1):
+ * logits / temperature, keep {z >= k-th largest} (top_k = 0: keep all), softmax, inverse-CDF draw over ascending token ids
+ * with u = (splitmix64(seed ^ step*0x9E3779B97F4A7C15 ^ row*0xD1B54A32D192ED03) >> 40 + 0.5) / 2^24 -- a counter-based
+ * generator, so a (seed, step, row) always draws the same token and the host can reproduce the draw.  do_sample = 0 restores
+ * greedy decoding. */
+int trace_b200_set_sampling(trace_b200_ctx* ctx, int do_sample, float temperature, int top_k, uint64_t seed);
+
+/* Teacher forcing for the NEXT trace_b200_decode call only (B and n must equal its batch and max_new): the ids written to
+ * ids_out are still the engine's own choices, but ids_host [B,n] are fed back instead (forward over a given continuation:
+ * per-step logits against a reference trace stay comparable after an fp16 tie).  NULL clears it. */
+int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int B, int n);
+
+/* Launch plan of the fused decode step at batch B and context length context_len: out8 = {attention splits per (row, kv
+ * head), combiner CTAs per (row, kv head), K/V page tiles per attention work item, k-phase width and stage width of the down
+ * projection, ring stages, row tiles per epilogue group, dynamic shared memory bytes}.  Tests use it to assert that the
+ * code paths of the full-size configurations (several K/V tiles per item, k-phased down projection) are the ones they run. */
+int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8);
+
 /* Introspection used by bench.py: kernels launched by this context since creation, and bytes of weights. */
 int64_t trace_b200_launch_count(trace_b200_ctx* ctx);
 int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);

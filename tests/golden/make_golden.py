@@ -72,7 +72,9 @@ def reference_generate(model, d, ids_rows, clips, ts_rows, heads, max_new, eos=2
     vis = model.encode_images_or_videos(list(clips), ["video"] * B, ts_rows)
     feats = model.get_model().get_vision_tower()(torch.stack(list(clips)).flatten(0, 1))
     heads = None if heads is None else list(heads)
-    out = model(inputs_embeds=embeds, attention_mask=mask2, use_cache=True, heads=heads, return_dict=True)
+    out = model(inputs_embeds=embeds, attention_mask=mask2, use_cache=True, heads=heads, return_dict=True,
+                output_hidden_states=True)
+    hid = out.hidden_states[-1]          # HF: last entry = after the final RMSNorm
     past = out.past_key_values
     finished = torch.zeros(B, dtype=torch.bool)
     gen, trace = [], []
@@ -94,7 +96,7 @@ def reference_generate(model, d, ids_rows, clips, ts_rows, heads, max_new, eos=2
         out = model(input_ids=tok[:, None], attention_mask=cur_mask, past_key_values=past, use_cache=True,
                     heads=heads, return_dict=True)
         past = out.past_key_values
-    return torch.stack(gen, 1), trace, {"embeds": embeds, "vis": vis, "feats": feats}
+    return torch.stack(gen, 1), trace, {"embeds": embeds, "vis": vis, "feats": feats, "hid": hid}
 
 
 def prompt_ids(d, L, seed):
@@ -113,7 +115,9 @@ def topk_pack(logit_row, lo, hi, k=8):
     return v.numpy().astype(np.float32), (i + lo).numpy().astype(np.int64)
 
 
-def make_case(ref, name, d, seed, B, T, L, heads0, max_new):
+def make_case(ref, name, d, seed, B, T, L, heads0, max_new, strides=(3, 8, 32, 64)):
+    """`heads0`: None (text-only logits), an int (every row starts on that head) or a list per row.
+    `strides` = (feats patch stride, feats width stride, vis width stride, embeds / hidden width stride)."""
     model = build_reference_model(ref, d, seed)
     clips, ts_rows, ids_rows = [], [], []
     for b in range(B):
@@ -121,7 +125,7 @@ def make_case(ref, name, d, seed, B, T, L, heads0, max_new):
         clips.append(px.float())
         ts_rows.append(ts)
         ids_rows.append(prompt_ids(d, L, 99 + b))
-    heads = None if heads0 is None else [heads0] * B
+    heads = None if heads0 is None else (list(heads0) if isinstance(heads0, (list, tuple)) else [heads0] * B)
     ids, trace, mid = reference_generate(model, d, ids_rows, clips, ts_rows, heads, max_new)
     ranges = [(0, d.time_base), (d.time_base, d.score_base), (d.score_base, d.total_vocab)]
     tv, ti, hh = [], [], []
@@ -134,7 +138,7 @@ def make_case(ref, name, d, seed, B, T, L, heads0, max_new):
             rv.append(v), ri.append(i), rh.append(h)
         tv.append(np.stack(rv)), ti.append(np.stack(ri)), hh.append(rh)
     meta = {"name": name, "dims": dataclasses.asdict(d), "seed": seed, "B": B, "T": T, "L": L,
-            "heads0": heads0, "max_new": max_new, "clip_seeds": [1234 + b for b in range(B)],
+            "heads0": heads0, "max_new": max_new, "strides": list(strides), "clip_seeds": [1234 + b for b in range(B)],
             "durations": [120.0 + 7.3 * b for b in range(B)], "prompt_seeds": [99 + b for b in range(B)],
             "transformers": __import__("transformers").__version__, "torch": torch.__version__}
     np.savez_compressed(
@@ -143,20 +147,44 @@ def make_case(ref, name, d, seed, B, T, L, heads0, max_new):
         out_ids=ids.numpy().astype(np.int64),
         top_vals=np.stack(tv), top_idx=np.stack(ti), step_heads=np.array(hh, dtype=np.int64),
         # strided samples of the intermediate seams (full tensors would be MBs)
-        feats_sample=mid["feats"][:, ::3, ::8].numpy().astype(np.float32),      # CLIP hidden_states[-2][:,1:]
-        vis_sample=mid["vis"][:, :, ::32].numpy().astype(np.float32),           # [B,14T,hidden/32]
-        embeds_sample=mid["embeds"][:, :, ::64].numpy().astype(np.float32),     # [B,S,hidden/64]
+        feats_sample=mid["feats"][:, ::strides[0], ::strides[1]].numpy().astype(np.float32),   # CLIP hidden_states[-2][:,1:]
+        vis_sample=mid["vis"][:, :, ::strides[2]].numpy().astype(np.float32),                  # [B,14T,hidden/stride]
+        embeds_sample=mid["embeds"][:, :, ::strides[3]].numpy().astype(np.float32),            # [B,S,hidden/stride]
+        hid_sample=mid["hid"][:, ::7, ::strides[3]].numpy().astype(np.float32),                # final-normed prefill hidden, every 7th position
+        hid_last=mid["hid"][:, -1, :].numpy().astype(np.float32),                              # [B,hidden] the row the first token is decoded from
         prefill_len=np.array(mid["embeds"].shape[1]))
     print(name, "ids", ids.tolist(), "S", mid["embeds"].shape[1])
+
+
+CASE_TABLE = {
+    "tiny_b1": lambda ref: make_case(ref, "tiny_b1", synth.tiny_dims(4), seed=0, B=1, T=4, L=12, heads0=1, max_new=24),
+    "tiny_b2": lambda ref: make_case(ref, "tiny_b2", synth.tiny_dims(4), seed=1, B=2, T=4, L=16, heads0=1, max_new=16),
+    "tiny_text": lambda ref: make_case(ref, "tiny_text", synth.tiny_dims(4), seed=2, B=1, T=4, L=12, heads0=None, max_new=8),
+    "mid_b1": lambda ref: make_case(ref, "mid_b1", synth.mid_dims(2), seed=3, B=1, T=2, L=20, heads0=1, max_new=12),
+    # full WIDTHS of BASELINE configs 2-5 (ViT 1024 x 16 heads x 336 px, hidden 4096, ffn 14336, vocab 32000) at shallow
+    # depth: every per-layer code path the full model takes (head partition over the whole vocabulary, k-phased down
+    # projection at batch 4/8, several K/V tiles per attention work item) is compared with the reference itself
+    "wide_b1": lambda ref: make_case(ref, "wide_b1", synth.wide_dims(8), seed=4, B=1, T=8, L=600, heads0=1, max_new=48,
+                                     strides=(24, 32, 128, 256)),
+    "wide_b4": lambda ref: make_case(ref, "wide_b4", synth.wide_dims(8), seed=5, B=4, T=8, L=600, heads0=[1, 0, 2, 0], max_new=32,
+                                     strides=(24, 32, 128, 256)),
+    "wide_b8": lambda ref: make_case(ref, "wide_b8", synth.wide_dims(8), seed=6, B=8, T=8, L=600,
+                                     heads0=[1, 0, 2, 1, 0, 2, 0, 1], max_new=24, strides=(24, 32, 128, 256)),
+    # context beyond 2304 positions (config 2 reaches 2527): 128 frames -> S = 2351
+    "wide_long_b1": lambda ref: make_case(ref, "wide_long_b1", synth.wide_dims(128), seed=7, B=1, T=128, L=560, heads0=0,
+                                          max_new=20, strides=(48, 64, 256, 512)),
+}
 
 
 def main():
     ref = load_reference()
     torch.manual_seed(0)
-    make_case(ref, "tiny_b1", synth.tiny_dims(4), seed=0, B=1, T=4, L=12, heads0=1, max_new=24)
-    make_case(ref, "tiny_b2", synth.tiny_dims(4), seed=1, B=2, T=4, L=16, heads0=1, max_new=16)
-    make_case(ref, "tiny_text", synth.tiny_dims(4), seed=2, B=1, T=4, L=12, heads0=None, max_new=8)
-    make_case(ref, "mid_b1", synth.mid_dims(2), seed=3, B=1, T=2, L=20, heads0=1, max_new=12)
+    names = sys.argv[1:] or list(CASE_TABLE)
+    for n in names:
+        import time
+        t0 = time.time()
+        CASE_TABLE[n](ref)
+        print(f"{n}: {time.time() - t0:.1f} s", flush=True)
 
 
 if __name__ == "__main__":

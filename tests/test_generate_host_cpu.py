@@ -9,10 +9,14 @@ from trace_b200.model import trace_mistral as tm
 
 class FakeEngine:
     max_ctx = 256
+    max_prefill_tokens = 4096
 
     def __init__(self, dims, device=0, **kw):
         self.dims, self.kw, self.log = dims, kw, []
         self._slot = 0
+
+    def set_sampling(self, do_sample, temperature=1.0, top_k=50, seed=0):
+        self.log.append(("sampling", bool(do_sample), float(temperature), int(top_k), int(seed)))
 
     def encode_frames(self, frames):
         self.log.append(("encode", tuple(frames.shape)))
@@ -109,8 +113,16 @@ def test_generate_error_behaviour(model):
     ids, clips, ts = _inputs(2)
     with pytest.raises(NotImplementedError):
         model.generate(ids, images_or_videos=clips, video_timestamps=ts, inputs_embeds=torch.zeros(1))      # trace_mistral.py:282-283
+    with pytest.raises(NotImplementedError):                                                                # training-only inputs
+        model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1, 1], times=[[1.0]], scores=[[2.0]])
+    bad = ids.clone()
+    bad[0, 3] = -203
+    with pytest.raises(NotImplementedError):                                                                # <time> placeholder without `times`
+        model.generate(bad, images_or_videos=clips, video_timestamps=ts, heads=[1, 1])
     with pytest.raises(NotImplementedError):
-        model.generate(ids, images_or_videos=clips, video_timestamps=ts, do_sample=True)
+        model.generate(ids, images_or_videos=clips, video_timestamps=ts, do_sample=True, top_p=0.9)
+    with pytest.raises(ValueError):                                                                         # text-only: placeholders are not ids
+        model.generate(ids, max_new_tokens=3)
     with pytest.raises(RuntimeError):                                                                       # torch.stack, trace_arch.py:222
         model.generate(ids, images_or_videos=[clips[0], clips[1][:2]], video_timestamps=ts, heads=[1, 1])
     with pytest.raises(AssertionError):                                                                     # trace_mistral.py:245
@@ -127,3 +139,34 @@ def test_generate_error_behaviour(model):
         model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1, 1], max_new_tokens=10_000)
     with pytest.raises(tm.TraceB200Error):                                                                  # forward needs the head weights
         model.forward(ids)
+
+
+def test_generate_sampling_arguments_reach_the_engine(model):
+    """scripts/inference/inference.py:62,71-73: do_sample=True, temperature=0.2 (generation_config: top_k=50)."""
+    ids, clips, ts = _inputs(1)
+    model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1], do_sample=True, temperature=0.2, max_new_tokens=3, seed=7)
+    assert ("sampling", True, 0.2, 50, 7) in [tuple(round(x, 6) if isinstance(x, float) else x for x in e) for e in model.engine.log]
+    model.engine.log.clear()
+    model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1], do_sample=False, temperature=0.0, max_new_tokens=3)
+    assert model.engine.log[0][:2] == ("sampling", False)
+    # without an explicit seed the draw follows torch's global generator (like HF's multinomial)
+    torch.manual_seed(3)
+    model.engine.log.clear()
+    model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1], do_sample=True, temperature=0.2, max_new_tokens=3)
+    s1 = model.engine.log[0][4]
+    torch.manual_seed(3)
+    model.engine.log.clear()
+    model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1], do_sample=True, temperature=0.2, max_new_tokens=3)
+    assert model.engine.log[0][4] == s1
+
+
+def test_prefill_groups_respect_the_workspace(model):
+    """Rows are prefilled in groups that fit max_prefill_tokens (a 128-frame batch of 8 does not fit the default 4096-token
+    workspace in one call): here S = 6 + 14*4 = 62, workspace 256 tokens -> groups of 4."""
+    ids, clips, ts = _inputs(6)
+    model.engine.max_prefill_tokens = 256
+    model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1] * 6, max_new_tokens=3)
+    assert [e[1] for e in model.engine.log if e[0] == "prefill"] == [4, 2]
+    model.engine.max_prefill_tokens = 40
+    with pytest.raises(tm.TraceB200Error):
+        model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1] * 6, max_new_tokens=3)

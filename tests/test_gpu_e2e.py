@@ -153,6 +153,7 @@ def test_graph_path_equals_eager_path():
     eng.close()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("TRACE_B200_DECODE") != "1", reason="TMEM reservoir is a switch of the round-1 decode kernel")
 @pytest.mark.parametrize("name", ["tiny_b2", "mid_b1"])
 def test_tmem_reservoir_is_bit_identical(name, monkeypatch):
     """The fused decode step parks weight-stream stages in tensor memory while it waits in grid barriers.  How many

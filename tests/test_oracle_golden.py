@@ -6,7 +6,7 @@ import torch
 
 from oracle import trace_oracle as orc
 from trace_b200 import synth
-from tests.util import CASES, load_case, ranges
+from tests.util import CASES, WIDE_CASES, load_case, ranges, row_heads0
 
 
 def test_known_answers_time_score():
@@ -44,6 +44,33 @@ def test_oracle_matches_reference(name):
             full = torch.full((d.total_vocab,), float("nan"))
             full[st["lo"]: st["lo"] + st["logits"].numel()] = st["logits"]
             np.testing.assert_allclose(full[idx].numpy(), z["top_vals"][s][b], atol=5e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name,rows,steps", [("wide_b1", [0], 16), ("wide_b4", [1, 2], 6)])
+def test_oracle_matches_reference_full_width(name, rows, steps):
+    """The oracle at the full widths of the BASELINE configs (shallow depth), pinned to the reference's own outputs: stage
+    samples, prefill hidden state, and the first decode steps of a few rows (the whole suite has to stay within minutes)."""
+    c = load_case(name)
+    d, z, meta = c["dims"], c["z"], c["meta"]
+    s0, s1, s2, s3 = meta["strides"]
+    o = orc.TraceOracle(d, synth.make_state_dict(d, meta["seed"]))
+    heads0 = row_heads0(meta)
+    T = meta["T"]
+    for b in rows:
+        ids, trace, mid = o.generate(c["prompt_ids"][b], c["clips"][b].float(), c["ts"][b], head=heads0[b], max_new_tokens=steps, return_trace=True)
+        feats = o.vit_features(c["clips"][b].float())
+        np.testing.assert_allclose(feats[:, ::s0, ::s1].numpy(), z["feats_sample"][b * T:(b + 1) * T], atol=5e-4, rtol=1e-4)
+        np.testing.assert_allclose(mid["vis"][:, ::s2].numpy(), z["vis_sample"][b], atol=5e-4, rtol=1e-4)
+        np.testing.assert_allclose(mid["prefill_embeds"][:, ::s3].numpy(), z["embeds_sample"][b], atol=5e-4, rtol=1e-4)
+        h, _ = o.llm_forward(mid["prefill_embeds"], None)
+        np.testing.assert_allclose(h[::7, ::s3].numpy(), z["hid_sample"][b], atol=2e-3, rtol=1e-3)
+        np.testing.assert_allclose(h[-1].numpy(), z["hid_last"][b], atol=2e-3, rtol=1e-3)
+        assert ids == z["out_ids"][b].tolist()[: len(ids)]
+        for s, st in enumerate(trace):
+            assert st["head"] == int(z["step_heads"][s][b])
+            full = torch.full((d.total_vocab,), float("nan"))
+            full[st["lo"]: st["lo"] + st["logits"].numel()] = st["logits"]
+            np.testing.assert_allclose(full[z["top_idx"][s][b]].numpy(), z["top_vals"][s][b], atol=2e-3, rtol=1e-4)
 
 
 def test_prefill_length_known_answer():

@@ -10,6 +10,16 @@ from trace_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["tiny_b1", "tiny_b2", "tiny_text", "mid_b1"]
+# full widths of the BASELINE configs at shallow depth (tests/golden/make_golden.py): outputs of the reference itself
+WIDE_CASES = ["wide_b1", "wide_b4", "wide_b8", "wide_long_b1"]
+
+
+def row_heads0(meta):
+    """Initial head per row (None, an int for every row, or a list)."""
+    h = meta["heads0"]
+    if h is None:
+        return None
+    return list(h) if isinstance(h, (list, tuple)) else [h] * meta["B"]
 
 
 def load_case(name):

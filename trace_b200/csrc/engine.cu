@@ -6,6 +6,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/trace_b200.h"
@@ -80,8 +81,10 @@ struct trace_b200_ctx {
   std::vector<std::vector<int>> slot_pages;
   std::vector<int> slot_len;
   std::vector<bool> slot_used;
-  // decode graphs keyed by batch
-  std::map<int, cudaGraphExec_t> graphs;
+  // streamed KV layout (decode_stream.cu): one pool per layer, [page][kv head][K|V][64][128], chunk-swizzled rows
+  std::vector<__half*> kv_pool;
+  // decode graphs.  v2: keyed by batch only (max_new / eos / pad / sampling live in device memory); v1 bakes them in
+  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
   // decode runs on an engine-owned stream (graph capture is illegal on the legacy default stream)
   cudaStream_t dstream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -94,6 +97,25 @@ struct trace_b200_ctx {
   bool fused_decode = true;
   int tm_relay = 0, gate_mode = 1, pf_ahead = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
   bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
+  // fused decode step, v2 (decode_stream.cu)
+  int decode_v = 2;               // TRACE_B200_DECODE=1 selects the round-1 kernel (decode_mega.cu) with its own KV layout
+  int cooperative = 1;
+  void* d_exchange = nullptr;
+  size_t exchange_bytes = 0;
+  unsigned* d_epoch = nullptr;
+  int64_t launches_since_reset = 0;
+  int* h_err = nullptr;           // mapped pinned host word: the kernel's watchdog writes it before it traps
+  int* d_err = nullptr;
+  int32_t* d_ctrl = nullptr;
+  int64_t* d_forced = nullptr;
+  float* d_samp_logits = nullptr;
+  DecodeStreamState sst{};
+  // sampling / teacher forcing set through the ABI, consumed by the next decode call
+  int do_sample = 0, top_k = 50;
+  float temperature = 1.0f;
+  uint64_t seed = 0;
+  std::vector<int64_t> forced_host;
+  int forced_B = 0, forced_n = 0;
 };
 
 namespace {
@@ -249,13 +271,42 @@ int allocate_all(trace_b200_ctx* ctx) {
     ctx->relay_sites = env_int("TRACE_B200_TM_SITES", 0, 63, 63);
     const char* env2 = getenv("TRACE_B200_ATTN_TC");
     ctx->attn_tc = (env2 != nullptr) ? atoi(env2) == 1 : true;   // tcgen05 attention: 2.0x (ViT) / 2.6x (prefill) the mma.sync kernel
+    ctx->decode_v = env_int("TRACE_B200_DECODE", 1, 2, 2);
+    ctx->cooperative = env_int("TRACE_B200_COOP", 0, 1, 1);
+    if (ctx->decode_v == 2) ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
   }
   // ---- KV pool ----
   const size_t page_elems = static_cast<size_t>(c.kv_heads) * kPage * c.head_dim;
   ctx->k_pool.resize(c.layers);
   ctx->v_pool.resize(c.layers);
-  for (int i = 0; i < c.layers; ++i)
-    if (dalloc(ctx, &ctx->k_pool[i], page_elems * c.kv_pages) || dalloc(ctx, &ctx->v_pool[i], page_elems * c.kv_pages)) return 1;
+  ctx->kv_pool.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    if (ctx->decode_v == 2) {
+      // zero-filled: a partially filled page is streamed whole and its unwritten rows meet probability 0 in P.V
+      if (dalloc(ctx, &ctx->kv_pool[i], 2 * page_elems * c.kv_pages, true)) return 1;
+    } else if (dalloc(ctx, &ctx->k_pool[i], page_elems * c.kv_pages) || dalloc(ctx, &ctx->v_pool[i], page_elems * c.kv_pages)) {
+      return 1;
+    }
+  }
+  if (ctx->decode_v == 2) {
+    size_t offs[8];
+    ctx->exchange_bytes = decode_stream_exchange_bytes(c.hidden, ctx->qkvw, c.heads * c.head_dim, c.ffn, ctx->num_sms, offs);
+    uint8_t* ex = nullptr;
+    if (dalloc(ctx, &ex, ctx->exchange_bytes, true)) return 1;
+    ctx->d_exchange = ex;
+    if (dalloc(ctx, &ctx->d_epoch, 1) || dalloc(ctx, &ctx->d_ctrl, 16, true) ||
+        dalloc(ctx, &ctx->d_forced, static_cast<size_t>(kMaxB) * c.max_ctx, true) ||
+        dalloc(ctx, &ctx->d_samp_logits, static_cast<size_t>(kMaxB) * ctx->total_vocab, true))
+      return 1;
+    const unsigned one = 1;
+    TB_CUDA(cudaMemcpy(ctx->d_epoch, &one, 4, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_err), 4, cudaHostAllocMapped));
+    *ctx->h_err = 0;
+    TB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_err), ctx->h_err, 0));
+    ctx->sst.pos = ctx->st.pos; ctx->sst.heads = ctx->st.heads; ctx->sst.finished = ctx->st.finished; ctx->sst.step = ctx->st.step;
+    ctx->sst.done_step = ctx->st.done_step; ctx->sst.out_ids = ctx->st.out_ids; ctx->sst.slot_ids = ctx->st.slot_ids;
+    ctx->sst.ctrl = ctx->d_ctrl; ctx->sst.forced = ctx->d_forced;
+  }
   if (dalloc(ctx, &ctx->d_block_table, static_cast<size_t>(kMaxSlots) * ctx->max_pages_seq, true)) return 1;
   ctx->h_block_table.assign(static_cast<size_t>(kMaxSlots) * ctx->max_pages_seq, 0);
   for (int i = c.kv_pages - 1; i >= 0; --i) ctx->free_pages.push_back(i);
@@ -418,8 +469,9 @@ int decoder_layers_prefill(trace_b200_ctx* ctx, int B, int S, const int32_t* slo
     const LlmLayer& l = ctx->llm[i];
     RUN(rmsnorm_f16(ctx->p_h, H, l.ln1, c.rms_eps, ctx->p_y, H, M, H, s));
     RUN(gemm_f16(ctx->p_y, H, l.qkv_w, H, ctx->p_qkv, ctx->qkvw, M, ctx->qkvw, H, nullptr, nullptr, 0, 0, 0, sms, s));
-    RUN(rope_kv_prefill(ctx->p_qkv, B, S, c.heads, c.kv_heads, c.head_dim, ctx->rope_cos, ctx->rope_sin, ctx->k_pool[i],
-                        ctx->v_pool[i], ctx->d_block_table, slot_ids_dev, ctx->max_pages_seq, kPage, s));
+    RUN(rope_kv_prefill(ctx->p_qkv, B, S, c.heads, c.kv_heads, c.head_dim, ctx->rope_cos, ctx->rope_sin,
+                        ctx->decode_v == 2 ? ctx->kv_pool[i] : ctx->k_pool[i], ctx->decode_v == 2 ? nullptr : ctx->v_pool[i],
+                        ctx->d_block_table, slot_ids_dev, ctx->max_pages_seq, kPage, s));
     if (ctx->attn_tc) {
       RUN(attention_tc_fwd(ctx->p_qkv, ctx->qkvw, ctx->p_attn, S, qd, static_cast<int64_t>(S) * qd, 0, qd, qd + kvd, c.heads,
                            c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
@@ -479,6 +531,136 @@ int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out,
   return 0;
 }
 
+DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out) {
+  const trace_b200_config& c = ctx->c;
+  DecodeStreamArgs a{};
+  a.B = B; a.H = c.hidden; a.qkvw = ctx->qkvw; a.qd = c.heads * c.head_dim; a.ffn = c.ffn; a.layers = layers_run; a.heads = c.heads;
+  a.kvh = c.kv_heads; a.vocab = c.vocab; a.head_rows = ctx->head_rows; a.n_valid = ctx->total_vocab; a.max_ctx = c.max_ctx;
+  a.num_sms = ctx->num_sms; a.page_size = kPage; a.max_pages = ctx->max_pages_seq; a.eps = c.rms_eps;
+  a.layer_table_dev = ctx->d_layer_table; a.final_norm = ctx->final_norm; a.head_w = ctx->head_w; a.x = ctx->d_x;
+  a.exchange = ctx->d_exchange; a.cos_tab = ctx->rope_cos; a.sin_tab = ctx->rope_sin; a.block_table = ctx->d_block_table;
+  a.logits_out = logits_out; a.samp_logits = ctx->d_samp_logits; a.embed = ctx->embed; a.time_tab = ctx->time_tab;
+  a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab; a.st = ctx->sst; a.epoch_ctr = ctx->d_epoch; a.err = ctx->d_err;
+  a.advance = layers_run > 0 ? 1 : 0; a.cooperative = ctx->cooperative; a.max_stages = ctx->max_stages; a.dbg = ctx->d_dbg;
+  return a;
+}
+
+// one launch of the streamed decode step (decode_stream.cu).  layers_run = 0: heads only, on the prefill's last hidden state
+int decode_step_v2(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, cudaStream_t s) {
+  const DecodeStreamArgs a = stream_args(ctx, B, layers_run, logits_out);
+  RUN(decode_stream_step(a, s));
+  return 0;
+}
+
+int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new, int eos, int pad,
+              int64_t* ids_out_host, int* n_out, float* logits_out_dev, cudaStream_t s) {
+  const trace_b200_config& c = ctx->c;
+  std::vector<int32_t> pos(B), zeros(kMaxB, 0);
+  for (int b = 0; b < B; ++b) pos[b] = ctx->slot_len[slots_host[b]];
+  int32_t ctrl[16] = {0};
+  ctrl[0] = max_new; ctrl[1] = eos; ctrl[2] = pad; ctrl[3] = ctx->do_sample;
+  memcpy(&ctrl[4], &ctx->temperature, 4);
+  ctrl[5] = ctx->top_k; ctrl[6] = static_cast<int32_t>(ctx->seed & 0xffffffffu); ctrl[7] = static_cast<int32_t>(ctx->seed >> 32);
+  const bool forced = !ctx->forced_host.empty();
+  if (forced) {
+    TB_CHECK(ctx->forced_B == B && ctx->forced_n == max_new, "forced ids were set for another batch size / max_new");
+    TB_CUDA(cudaMemcpyAsync(ctx->d_forced, ctx->forced_host.data(), ctx->forced_host.size() * 8, cudaMemcpyHostToDevice, s));
+    ctrl[8] = 1;
+  }
+  // exchange epochs are 32-bit (512 per launch): long before they wrap, clear the buffers and restart the counter
+  if (ctx->launches_since_reset > (1 << 22)) {
+    const unsigned one = 1;
+    TB_CUDA(cudaMemsetAsync(ctx->d_exchange, 0, ctx->exchange_bytes, s));
+    TB_CUDA(cudaMemcpyAsync(ctx->d_epoch, &one, 4, cudaMemcpyHostToDevice, s));
+    ctx->launches_since_reset = 0;
+  }
+  TB_CUDA(cudaMemcpyAsync(ctx->d_ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.heads, heads_inout_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.finished, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->st.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaStreamSynchronize(s));     // ctrl / pos / forced_host are host stack or heap memory
+  ctx->forced_host.clear();
+  const size_t lstride = static_cast<size_t>(B) * ctx->total_vocab;
+
+  auto fail = [&](cudaError_t e, const char* what) -> int {
+    tb::set_error(std::string(what) + " failed: " + cudaGetErrorString(e) + " (decode watchdog word " + std::to_string(*ctx->h_err) +
+                  ": code*1000 + CTA; 21/22 activation wait, 31-33 ring, 41-44 attention exchange, 51 candidates)");
+    return 1;
+  };
+  int done = 0;
+  auto poll_done = [&]() -> int {
+    cudaError_t e = cudaMemcpyAsync(&done, ctx->st.done_step, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(e, "decode step");
+    return 0;
+  };
+  TB_CUDA(cudaEventRecord(ctx->ev_t0, s));
+  // token 0: heads on the prefill's last hidden state, no decoder pass, positions do not advance
+  if (decode_step_v2(ctx, B, 0, logits_out_dev, s)) return 1;
+  ++ctx->launches_since_reset;
+  int steps_run = 1;
+  if (logits_out_dev != nullptr || max_new <= 2) {
+    // instrumented path: one eager step per token (parity tests read every step's logits)
+    for (; steps_run < max_new; ++steps_run) {
+      if (poll_done()) return 1;
+      if (done) break;
+      if (decode_step_v2(ctx, B, c.layers, logits_out_dev ? logits_out_dev + lstride * steps_run : nullptr, s)) return 1;
+      ++ctx->launches_since_reset;
+    }
+  } else {
+    // production path: step 1 eager (also sets kernel attributes), then one captured step replayed.  Nothing that varies
+    // between calls (max_new, eos, pad, sampling, forced ids) is a kernel parameter, so the graph is keyed by batch only.
+    if (decode_step_v2(ctx, B, c.layers, nullptr, s)) return 1;
+    ++steps_run;
+    cudaGraphExec_t exec = nullptr;
+    const auto gkey = std::make_tuple(B, 0, 0, 0);
+    auto it = ctx->graphs.find(gkey);
+    if (it != ctx->graphs.end()) {
+      exec = it->second;
+    } else {
+      cudaGraph_t graph = nullptr;
+      TB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = ctx->launches;
+      const int rc = decode_step_v2(ctx, B, c.layers, nullptr, s);
+      ctx->launches = before;
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      TB_CHECK(rc == 0, std::string("decode step failed during graph capture: ") + tb::get_error());
+      TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+      TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      ctx->graphs[gkey] = exec;
+    }
+    while (steps_run < max_new) {
+      const int burst = (max_new - steps_run < 16) ? (max_new - steps_run) : 16;
+      for (int i = 0; i < burst; ++i) TB_CUDA(cudaGraphLaunch(exec, s));
+      steps_run += burst;
+      ctx->launches += burst;
+      ctx->launches_since_reset += burst;
+      if (poll_done()) return 1;
+      if (done) break;
+    }
+  }
+  TB_CUDA(cudaEventRecord(ctx->ev_t1, s));
+  if (poll_done()) return 1;
+  TB_CHECK(*ctx->h_err == 0, "decode watchdog fired: " + std::to_string(*ctx->h_err));
+  TB_CUDA(cudaEventElapsedTime(&ctx->last_decode_ms, ctx->ev_t0, ctx->ev_t1));
+  ctx->last_decode_steps = steps_run;
+  const int n = done ? done : (steps_run < max_new ? steps_run : max_new);
+  std::vector<int64_t> tmp(static_cast<size_t>(B) * max_new);
+  TB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->st.out_ids, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaMemcpyAsync(heads_inout_host, ctx->st.heads, B * 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b) {
+    memcpy(ids_out_host + static_cast<size_t>(b) * max_new, tmp.data() + static_cast<size_t>(b) * max_new, static_cast<size_t>(n) * 8);
+    ctx->slot_len[slots_host[b]] += n - 1;
+  }
+  *n_out = n;
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -527,6 +709,7 @@ void trace_b200_destroy(trace_b200_ctx* ctx) {
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->h_err) cudaFreeHost(ctx->h_err);
   delete ctx;
 }
 
@@ -544,13 +727,15 @@ int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
   TB_CHECK(ctx != nullptr, "null context");
   for (const std::string& n : ctx->expected) TB_CHECK(ctx->loaded.count(n) == 1, "missing weight " + n);
   {
-    TB_CHECK(decode_mega_layer_table_bytes() == 8 * static_cast<int>(sizeof(void*)), "layer table layout mismatch");
+    TB_CHECK(decode_mega_layer_table_bytes() == 8 * static_cast<int>(sizeof(void*)) && decode_stream_layer_bytes() == 8 * static_cast<int>(sizeof(void*)),
+             "layer table layout mismatch");
     std::vector<const void*> tab;
     for (int i = 0; i < ctx->c.layers; ++i) {
       const LlmLayer& l = ctx->llm[i];
+      const void* p6 = ctx->decode_v == 2 ? static_cast<const void*>(ctx->kv_pool[i]) : static_cast<const void*>(ctx->k_pool[i]);
+      const void* p7 = ctx->decode_v == 2 ? nullptr : static_cast<const void*>(ctx->v_pool[i]);
       for (const void* q : {static_cast<const void*>(l.ln1), static_cast<const void*>(l.qkv_w), static_cast<const void*>(l.o_w),
-                            static_cast<const void*>(l.ln2), static_cast<const void*>(l.gateup_w), static_cast<const void*>(l.down_w),
-                            static_cast<const void*>(ctx->k_pool[i]), static_cast<const void*>(ctx->v_pool[i])})
+                            static_cast<const void*>(l.ln2), static_cast<const void*>(l.gateup_w), static_cast<const void*>(l.down_w), p6, p7})
         tab.push_back(q);
     }
     if (ctx->d_layer_table == nullptr) {
@@ -673,6 +858,8 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
     pos[b] = ctx->slot_len[sl];
   }
   TB_CHECK(max_new <= c.max_ctx, "max_new exceeds the output buffer");
+  if (ctx->decode_v == 2) return decode_v2(ctx, slots_host, B, heads_inout_host, max_new, eos, pad, ids_out_host, n_out, logits_out_dev, s);
+  TB_CHECK(ctx->do_sample == 0 && ctx->forced_host.empty(), "sampling / forced ids need the streamed decode step (TRACE_B200_DECODE=2)");
   ctx->st.max_new = max_new;
   TB_CUDA(cudaMemcpyAsync(ctx->st.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->st.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
@@ -708,7 +895,8 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
     if (decode_step(ctx, B, eos, pad, nullptr, s)) return 1;
     ++steps_run;
     cudaGraphExec_t exec = nullptr;
-    auto it = ctx->graphs.find(B);
+    const auto gkey = std::make_tuple(B, max_new, eos, pad);   // the captured v1 nodes bake these in as kernel parameters
+    auto it = ctx->graphs.find(gkey);
     if (it != ctx->graphs.end()) {
       exec = it->second;
     } else {
@@ -722,7 +910,7 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
       TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("graph capture failed: ") + cudaGetErrorString(ce));
       TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      ctx->graphs[B] = exec;
+      ctx->graphs[gkey] = exec;
     }
     while (steps_run < max_new) {
       const int burst = (max_new - steps_run < 16) ? (max_new - steps_run) : 16;
@@ -748,6 +936,33 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   }
   *n_out = n;
   return 0;
+}
+
+int trace_b200_set_sampling(trace_b200_ctx* ctx, int do_sample, float temperature, int top_k, uint64_t seed) {
+  TB_CHECK(ctx != nullptr, "null context");
+  TB_CHECK(!do_sample || temperature > 0.f, "temperature must be positive");
+  TB_CHECK(top_k >= 0, "top_k must be >= 0 (0 = off)");
+  ctx->do_sample = do_sample ? 1 : 0;
+  ctx->temperature = do_sample ? temperature : 1.0f;
+  ctx->top_k = top_k;
+  ctx->seed = seed;
+  return 0;
+}
+
+int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int B, int n) {
+  TB_CHECK(ctx != nullptr, "null context");
+  if (ids_host == nullptr || B == 0) { ctx->forced_host.clear(); return 0; }
+  TB_CHECK(B >= 1 && B <= kMaxB && n >= 1 && n <= ctx->c.max_ctx, "bad forced-id shape");
+  ctx->forced_host.assign(ids_host, ids_host + static_cast<size_t>(B) * n);
+  ctx->forced_B = B;
+  ctx->forced_n = n;
+  return 0;
+}
+
+int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8) {
+  TB_CHECK(ctx != nullptr && out8 != nullptr, "null argument");
+  TB_CHECK(ctx->decode_v == 2, "decode plan introspection needs the streamed decode step (TRACE_B200_DECODE=2)");
+  return decode_stream_plan(stream_args(ctx, B, ctx->c.layers, nullptr), context_len, out8);
 }
 
 int64_t trace_b200_launch_count(trace_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -65,6 +65,14 @@ int preprocess_frames(const uint8_t* frames, int F, int H, int W, int S, int pad
                       const int32_t* vcoef, int vk, const float* mean, const float* stdv, const int* pad_rgb, uint8_t* tmp, __half* out,
                       cudaStream_t stream);
 
+// ---- paged KV cache, streamed layout (rope_kv.cu writes it at prefill, decode_stream.cu appends and reads) ----
+// one pool per layer: [page][kv_head][K|V][page_size positions][hd] fp16; element offset of a (page, kv head, K/V) tile:
+__host__ __device__ inline int64_t kv_tile_offset(int page, int kvh, int kv, int is_v, int page_size, int hd) {
+  return ((static_cast<int64_t>(page) * kvh + kv) * 2 + is_v) * page_size * hd;
+}
+// column of element d of the row at in-page position pos: 16-byte chunks (8 halves) are XOR-swizzled with pos & 7
+__host__ __device__ inline int kv_chunk_swz(int d, int pos) { return (((d >> 3) ^ (pos & 7)) << 3) | (d & 7); }
+
 // ---- decode.cu -------------------------------------------------------------------------------------------
 struct DecodeState {           // device-resident generation state (no host round trips inside the loop)
   int32_t* pos;                // [B] number of cached positions (== position id of the token being fed)
@@ -130,5 +138,37 @@ struct DecodeMegaArgs {
 };
 int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream);
 int decode_mega_layer_table_bytes();
+
+// ---- decode_stream.cu : the decode step as one cooperative kernel, one HBM stream (weights + K/V pages), flag-in-data exchanges ----
+struct DecodeStreamState {     // device-resident generation state; nothing in it is baked into a captured graph
+  int32_t *pos, *heads, *finished, *step, *done_step;
+  int64_t* out_ids;            // [B, ctrl[0]]
+  int32_t* slot_ids;           // [B]
+  int32_t* ctrl;               // [16]: 0 max_new, 1 eos, 2 pad, 3 do_sample, 4 temperature (float bits), 5 top_k, 6/7 seed lo/hi, 8 use_forced
+  const int64_t* forced;       // [B, ctrl[0]] teacher-forced ids (fed back instead of the chosen token when ctrl[8])
+};
+struct DecodeStreamArgs {
+  int B, H, qkvw, qd, ffn, layers, heads, kvh, vocab, head_rows, n_valid, max_ctx, num_sms, page_size, max_pages;
+  float eps;
+  const void* layer_table_dev;   // [layers] x {ln1, qkv_w, o_w, ln2, gateup_w, down_w, kv_pool, -} device pointers
+  const __half *final_norm, *head_w;
+  __half* x;                     // [B,H] dense: input embedding of this step in, of the next step out
+  void* exchange;                // zero-initialised, decode_stream_exchange_bytes() bytes
+  const float *cos_tab, *sin_tab;
+  const int32_t* block_table;
+  float* logits_out;             // [B, n_valid] masked logits of this step (instrumented path) or null
+  float* samp_logits;            // [B, n_valid] scratch for sampling
+  const __half *embed, *time_tab, *score_tab, *sync_tab;
+  DecodeStreamState st;
+  unsigned* epoch_ctr;           // device launch counter (starts at 1); exchange epochs derive from it
+  int* err;                      // device error word written by the kernel's watchdog before it traps
+  int advance;                   // 0: head-only launch on the prefill's last hidden state (layers must be 0), 1: a decoder pass
+  int cooperative, max_stages;
+  unsigned long long* dbg;
+};
+int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream);
+int decode_stream_plan(const DecodeStreamArgs& a, int t, int32_t* out /*[8]: nsplit, ncomb, K/V pages per attention item at context t, kp_down, ks_down, ring stages, tiles per epilogue group, smem bytes*/);
+size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sms, size_t* offs /*[8]*/);
+int decode_stream_layer_bytes();
 
 }  // namespace tb

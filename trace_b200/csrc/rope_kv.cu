@@ -2,7 +2,11 @@
 // Operates in place on the fused qkv activation [B*S, (heads + 2*kvh) * hd] produced by the QKV GEMM:
 // q and k columns are rotated (rotate_half pairs d, d+hd/2; cos/sin tables hold the fp16-rounded values the
 // reference casts to, [max_pos, hd/2]); rotated k and raw v rows are appended to the page pool
-//   K/V pool layout: [page][kv_head][page_size][hd] fp16, page = block_table[slot][pos / page_size].
+//   legacy layout (v_pool != nullptr): two pools [page][kv_head][page_size][hd] fp16, page = block_table[slot][pos / page_size].
+//   streamed layout (v_pool == nullptr, the default): ONE pool [page][kv_head][K|V][page_size][hd]; the 16-byte chunks of
+//   a row are stored at chunk ^ (pos & 7).  A (page, kv head) tile is then one contiguous 32 KB block that the fused decode
+//   step pulls into shared memory with a single cp.async.bulk, and both the mma.sync B-fragment reads of K and the
+//   ldmatrix.trans reads of V are bank-conflict free without padding (kv_tile_offset / kv_chunk_swz in kernels.h).
 // One CTA per token; HBM-bound: reads+writes the qkv row once, writes 2*kvh*hd halves to the pool.
 #include "common.cuh"
 #include "kernels.h"
@@ -34,15 +38,23 @@ rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, cons
     p[d] = ra;
     p[d + hh] = rb;
     if (h >= heads) {
-      __half* kd = k_pool + ((static_cast<int64_t>(page) * kvh + (h - heads)) * page_size + poff) * hd;
-      kd[d] = ra;
-      kd[d + hh] = rb;
+      if (v_pool != nullptr) {
+        __half* kd = k_pool + ((static_cast<int64_t>(page) * kvh + (h - heads)) * page_size + poff) * hd;
+        kd[d] = ra;
+        kd[d + hh] = rb;
+      } else {
+        __half* kd = k_pool + kv_tile_offset(page, kvh, h - heads, 0, page_size, hd) + static_cast<int64_t>(poff) * hd;
+        kd[kv_chunk_swz(d, poff)] = ra;
+        kd[kv_chunk_swz(d + hh, poff)] = rb;
+      }
     }
   }
   const __half* vsrc = row + (heads + kvh) * hd;
   for (int i = threadIdx.x; i < kvh * hd / 8; i += blockDim.x) {
     const int h = (i * 8) / hd, d = (i * 8) % hd;
-    __half* vd = v_pool + ((static_cast<int64_t>(page) * kvh + h) * page_size + poff) * hd + d;
+    __half* vd = (v_pool != nullptr)
+                     ? v_pool + ((static_cast<int64_t>(page) * kvh + h) * page_size + poff) * hd + d
+                     : k_pool + kv_tile_offset(page, kvh, h, 1, page_size, hd) + static_cast<int64_t>(poff) * hd + kv_chunk_swz(d, poff);
     *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vsrc + i * 8);
   }
 }

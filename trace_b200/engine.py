@@ -22,7 +22,7 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
     "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
 ]
 
@@ -67,6 +67,9 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_prefill.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), i32, vp, i32, vp, vp]
     lib.trace_b200_decode.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), i32, ctypes.POINTER(ctypes.c_int32), i32, i32,
                                       i32, ctypes.POINTER(i64), ctypes.POINTER(i32), vp, vp]
+    lib.trace_b200_set_sampling.argtypes = [vp, i32, f32, i32, ctypes.c_uint64]
+    lib.trace_b200_set_forced_ids.argtypes = [vp, ctypes.POINTER(i64), i32, i32]
+    lib.trace_b200_decode_plan.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_int32)]
     lib.trace_b200_launch_count.argtypes = [vp]
     lib.trace_b200_launch_count.restype = i64
     lib.trace_b200_last_decode_timing.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
@@ -122,6 +125,7 @@ class Engine:
                            dims.vit_ln_eps, dims.hidden, dims.layers, dims.heads, dims.kv_heads, dims.head_dim, dims.ffn,
                            dims.vocab, dims.rope_theta, dims.rms_eps, vit_chunk_frames, max_prefill_tokens, max_ctx, kv_pages)
         self.max_ctx = max_ctx
+        self.max_prefill_tokens = max_prefill_tokens
         h = ctypes.c_void_p()
         with torch.cuda.device(device):
             _check(self.lib.trace_b200_create(ctypes.byref(self.cfg), device, ctypes.byref(h)))
@@ -196,11 +200,21 @@ class Engine:
         _check(self.lib.trace_b200_prefill(self._h, arr, B, e.data_ptr(), S, _ptr(hid), _stream()))
         return hid
 
+    def set_sampling(self, do_sample: bool, temperature: float = 1.0, top_k: int = 50, seed: int = 0) -> None:
+        """HF `_sample` with the default warpers (temperature, top-k) for the following decode() calls; see trace_b200.h."""
+        _check(self.lib.trace_b200_set_sampling(self._h, int(bool(do_sample)), float(temperature), int(top_k), int(seed) & (2 ** 64 - 1)))
+
     def decode(self, slots: Sequence[int], heads: List[int], max_new: int, eos: int = 2, pad: int = 2,
-               return_logits: bool = False):
-        """Greedy loop.  `heads` is mutated in place (as the reference mutates its `heads` list).
+               return_logits: bool = False, forced_ids=None):
+        """Greedy (or sampled, see set_sampling) loop.  `heads` is mutated in place (as the reference mutates its `heads`
+        list).  `forced_ids` [B, max_new]: teacher forcing -- the returned ids are still the engine's own choices.
         Returns ids [B, n] int64 (CPU) and optionally the masked logits [n, B, vocab+27] (CUDA fp32)."""
         B = len(slots)
+        if forced_ids is not None:
+            f = torch.as_tensor(forced_ids, dtype=torch.int64).contiguous()
+            assert tuple(f.shape) == (B, max_new), f"forced ids must be [B, max_new], got {tuple(f.shape)}"
+            arr = (ctypes.c_int64 * (B * max_new))(*f.flatten().tolist())
+            _check(self.lib.trace_b200_set_forced_ids(self._h, arr, B, max_new))
         sl = (ctypes.c_int32 * B)(*slots)
         hd = (ctypes.c_int32 * B)(*heads)
         ids = (ctypes.c_int64 * (B * max_new))()
@@ -216,6 +230,12 @@ class Engine:
         if return_logits:
             return out, logits[: n.value]
         return out
+
+    def decode_plan(self, B: int, context_len: int) -> dict:
+        out = (ctypes.c_int32 * 8)()
+        _check(self.lib.trace_b200_decode_plan(self._h, B, context_len, out))
+        keys = ("nsplit", "ncomb", "kv_tiles_per_item", "kp_down", "ks_down", "stages", "group_tiles", "smem_bytes")
+        return dict(zip(keys, list(out)))
 
     @property
     def launch_count(self) -> int:

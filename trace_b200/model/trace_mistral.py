@@ -229,9 +229,13 @@ class TraceMistralForCausalLM:
         S = L if slots is None else L - 1 + self.dims.tokens_per_frame * T
         if S + max_new > self.engine.max_ctx:
             raise TraceB200Error(f"prompt ({S}) + max_new_tokens ({max_new}) exceeds the engine context ({self.engine.max_ctx})")
+        if S > self.engine.max_prefill_tokens:
+            raise TraceB200Error(f"prompt ({S}) exceeds the engine's prefill workspace ({self.engine.max_prefill_tokens} tokens)")
+        # rows per prefill + decode group: the decode batch limit and what the prefill workspace holds
+        group = max(1, min(8, self.engine.max_prefill_tokens // S))
         n_final = 0
-        for b0 in range(0, B, 8):
-            b1 = min(B, b0 + 8)
+        for b0 in range(0, B, group):
+            b1 = min(B, b0 + group)
             if slots is None:
                 embeds = self.engine.build_prefill(ids[b0:b1].contiguous(), None, None)
             else:
@@ -266,16 +270,30 @@ class TraceMistralForCausalLM:
         kwargs.pop("position_ids", None)
         heads = kwargs.pop("heads", None)
         max_new = kwargs.pop("max_new_tokens", None) or 20
-        do_sample = kwargs.pop("do_sample", False)
-        kwargs.pop("temperature", None)
+        do_sample = bool(kwargs.pop("do_sample", False))
+        temperature = kwargs.pop("temperature", None)
+        top_k = kwargs.pop("top_k", None)
+        top_p = kwargs.pop("top_p", None)
+        seed = kwargs.pop("seed", None)
         kwargs.pop("use_cache", None)
         kwargs.pop("stopping_criteria", None)   # constructed by every driver, only trace/__init__.py passes it
         pad = kwargs.pop("pad_token_id", None)
         eos = kwargs.pop("eos_token_id", None) or self.generation_config.eos_token_id
         if pad is None:
             pad = eos
+        if times or scores:
+            # training-time inputs: the reference embeds them at the -203 / -204 placeholders (trace_arch.py:423-426)
+            raise NotImplementedError("`times` / `scores` (the <time>/<score> placeholders of training prompts) are not part of the inference path")
         if do_sample:
-            raise NotImplementedError("trace_b200 implements the greedy path of the BASELINE configs (do_sample=False)")
+            # HF `_sample` with the default warpers, as scripts/inference/inference.py:62,71-73 drives it (T=0.2, top_k=50)
+            if top_p is not None and float(top_p) < 1.0:
+                raise NotImplementedError("top_p < 1 is not implemented (no TRACE driver sets it)")
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # follows torch.manual_seed like HF's multinomial
+            self.engine.set_sampling(True, 1.0 if temperature is None else float(temperature),
+                                     50 if top_k is None else int(top_k), seed)
+        else:
+            self.engine.set_sampling(False)
         assert inputs is not None and inputs.dim() == 2
         B, L = inputs.shape
         if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
@@ -285,6 +303,8 @@ class TraceMistralForCausalLM:
         if images_or_videos is None:
             # plain text generate: inputs_embeds = embed_tokens(inputs) (trace_mistral.py:306-307)
             ids = inputs.to(self.device, torch.int64).contiguous()
+            if bool(((ids < 0) | (ids >= self.vocab_size + 27)).any()):
+                raise ValueError("text-only generate: ids must be plain token ids (no multimodal placeholders, < vocab + 27)")
             return self._generate_from_slots(ids, None, None, heads, max_new, eos, pad).to(inputs.device)
         modal_list = modal_list or ["video"] * B
         nf = self.num_frames()
@@ -295,6 +315,10 @@ class TraceMistralForCausalLM:
         ids = inputs.to(self.device, torch.int64).contiguous()
         nvid = ((ids == MMODAL_TOKEN_INDEX["VIDEO"]) | (ids == MMODAL_TOKEN_INDEX["IMAGE"])).sum(1)
         assert bool((nvid == 1).all()), "only have one video inputs!"                            # trace_arch.py:408
+        if bool(((ids == MMODAL_TOKEN_INDEX["TIME"]) | (ids == MMODAL_TOKEN_INDEX["SCORE"])).any()):
+            raise NotImplementedError("<time>/<score> placeholders need `times` / `scores` (training prompts), not part of the inference path")
+        if bool((ids >= self.vocab_size + 27).any()):
+            raise ValueError("token id out of range")
         if video_timestamps is None:
             raise NotImplementedError("video_timestamps=None (no time rows) is not used by any TRACE driver")
         tid = torch.tensor([frame_time_ids(ts) for ts in video_timestamps], dtype=torch.int32, device=self.device)

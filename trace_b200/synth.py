@@ -105,6 +105,13 @@ def mid_dims(num_frames: int = 8) -> TraceDims:
                      num_frames=num_frames)
 
 
+def wide_dims(num_frames: int = 8) -> TraceDims:
+    """Full widths of the BASELINE configs (CLIP-ViT-L/14-336 and Mistral-7B layer shapes, full vocabulary) at shallow
+    depth (3 ViT blocks of which 2 are used, 2 decoder layers): the real reference finishes it on CPU in minutes, and
+    every per-layer code path of the full model is taken."""
+    return TraceDims(vit_layers=3, layers=2, num_frames=num_frames)
+
+
 # ------------------------------------------------------------------------------------------------
 # parameter inventory
 # ------------------------------------------------------------------------------------------------
