@@ -3,21 +3,25 @@
 
 One "step" = the whole hot path over one clip per GPU: CLIP-ViT-L/14-336 encode of 128 frames -> spatial-slot
 projector -> prompt splice -> Mistral-7B prefill (S = 14*128 + 224 - 1 = 2015) -> greedy decode of 512 new tokens
-with the three interleaved heads, through the reference-shaped surface `TraceMistralForCausalLM.generate`.
+with the three interleaved heads, through the package's public surface: `TraceMistralForCausalLM.generate` on one GPU,
+`trace_b200.parallel.generate_sharded` on N GPUs.
 
-  value : whole-job events/s with the clip already resident in HBM when the timed region starts
-  e2e   : the same metric with the clip in pinned HOST memory (H2D copy + D2H of the ids inside the timed region)
-  roofline : the decode step (32 x {QKV, attention, O, gate/up, down} + head + finalize = one CUDA-graph replay),
-             HBM-bound: algorithmic bytes per step / mean device time per step measured with CUDA events on the
-             engine's decode stream inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  value : whole-job events/s with the clips already resident in HBM when the timed region starts
+  e2e   : the same metric with the clips in pinned HOST memory (H2D copy + D2H of the ids inside the timed region)
+  roofline : the decode step (one cooperative kernel per generated token: 32 x {QKV, attention, O, gate/up, down} + heads +
+             argmax / head switch), HBM-bound: algorithmic bytes per step / mean device time per step measured with CUDA
+             events on the engine's decode stream inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  batched : the batched configurations BASELINE.json names, each with its own roofline --
+             config 3 (one GPU, 8 x 64-frame clips, moment-retrieval prompt) and config 4 (4 x 128-frame clips per GPU;
+             at N GPUs 4N clips through generate_sharded: ViT frame-sharded 128/N frames per GPU + one all-gather).
   cpu_baseline : the CPU oracle (port of the reference path) timed on the host cores on a bounded sample.
 
-N > 1 (torchrun, one rank per GPU, NCCL): every rank owns one clip per step (weak scaling); each clip's 128
-frames are split 128/N per rank through CLIP + projector and ONE all-gather of the projected slot tokens
-rebuilds the clip on every rank; prefill + decode are replicated per clip.
+N > 1 (torchrun, one rank per GPU, NCCL): one clip per rank per step (weak scaling).  Every clip's 128 frames are split
+128/N per rank through CLIP + projector -- a rank uploads only ITS frames of every clip -- and ONE all-gather of the projected
+slot tokens rebuilds the clips on every rank; rank r prefills + decodes clip r.
 
-`--impl reference` times the CPU oracle port (oracle/trace_oracle.py, a restatement of the reference's PyTorch
-path; /root/reference itself does not exist on the GPU box) with all host threads on a bounded sample per step.
+`--impl reference` times the CPU oracle port (oracle/trace_oracle.py, a restatement of the reference's PyTorch path;
+/root/reference itself does not exist on the GPU box) with the host threads each stage can use, one bounded sample per step.
 """
 from __future__ import annotations
 
@@ -37,9 +41,12 @@ import torch  # noqa: E402
 TOKENS_PER_EVENT = 40     # synth.TOKENS_PER_EVENT: 13 time + 4 score + 22 caption + 1 <sync>
 L_TEXT = 224              # fixed prompt length
 MAX_NEW = 512             # evaluate.py:449
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_step_kernel launch (ncu, B=1, context ~2020), see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = 14245.12e6 + 118.06e6
-NCU_DRAM_SOURCE = "profiles/r01_ncu_full_decode_step_final.csv (ncu --set full, one decode_step_kernel<1> launch, context 2017)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE decode step launch (ncu --set full, B=1); None until a capture of the
+# current kernel is committed under profiles/
+NCU_DRAM = {"bytes": None, "source": None}
+_ncu = os.path.join(ROOT, "profiles", "r02_decode_step_dram.json")
+if os.path.exists(_ncu):
+    NCU_DRAM = json.load(open(_ncu))
 
 
 def parse_args():
@@ -52,6 +59,7 @@ def parse_args():
     ap.add_argument("--max-new", type=int, default=MAX_NEW)
     ap.add_argument("--weights", default="structured", choices=["structured", "random"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-batched", action="store_true")
     return ap.parse_args()
 
 
@@ -63,13 +71,15 @@ def peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-def bench_prompt_ids(T):
-    """llama_2 template + <video>\\n + trace/prompts/dvc.txt + <sync>, stand-in tokenizer, padded to L_TEXT ids."""
+def bench_prompt_ids(T, task="dvc"):
+    """llama_2 template + <video>\\n + the task prompt (trace/prompts/dvc.txt or mr.txt) + <sync>, stand-in tokenizer,
+    padded to L_TEXT ids."""
     from trace_b200 import prompts, synth
     from trace_b200.conversation import conv_templates
     from trace_b200.mm_utils import tokenizer_MMODAL_token_all
+    text = prompts.DVC if task == "dvc" else prompts.MR.format("a person opens the door and walks into the room")
     conv = conv_templates["llama_2"].copy()
-    conv.append_message(conv.roles[0], "<video>\n" + prompts.DVC)
+    conv.append_message(conv.roles[0], "<video>\n" + text)
     conv.append_message(conv.roles[1], None)
     ids = tokenizer_MMODAL_token_all(conv.get_prompt() + "<sync>", synth.StandInTokenizer(), return_tensors="pt").tolist()
     filler = [3 + (7919 * i) % 31000 for i in range(max(0, L_TEXT - len(ids)))]
@@ -123,94 +133,128 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(T, max_new, threads):
-    """Bounded sample of the same workload on the host cores with the oracle port, scaled to events/s.
+class CpuSampler:
+    """Bounded sample of config 2 on the host cores with the oracle port, scaled to events/s.
 
-    Sample: 2 frames through 1 CLIP block (x23 blocks x T/2), 1 decoder layer prefill at S=2015 (x32), 4 decode tokens
-    through 1 decoder layer at t~2015 (x32 layers x max_new tokens) + 1 text-head evaluation (x text-head steps).
-    Full widths, fp32, depth scaled linearly -- stated in the JSON as `sample`."""
-    from oracle import trace_oracle as orc
-    from trace_b200 import synth
-    import dataclasses
-    torch.set_num_threads(threads)
-    full = synth.full_dims(T)
-    d = dataclasses.replace(full, vit_layers=2, layers=1)          # 1 executed CLIP block, 1 decoder layer
-    sd = {}
-    for name, shape, kind in synth.param_specs(d):
-        if name in ("model.embed_tokens.weight",):
-            sd[name] = torch.zeros(shape)                          # gathers only; no need to randomise 131M values
-        else:
-            sd[name] = synth.synth_tensor(name, shape, kind, 0).float()
-    o = orc.TraceOracle(d, sd)
-    px, _ = synth.synthetic_clip(d, 2)
-    # thread count: all host threads the path can USE -- torch's intra-op pool degrades badly when oversubscribed on
-    # many-core boxes (128 threads on the GEMV-shaped decode step), so calibrate on one decode token and keep the best
-    e1 = torch.randn(1, d.hidden) * 0.02
-    _, c1 = o.llm_forward(torch.randn(64, d.hidden) * 0.02, None)
-    best = (1e9, threads)
-    for nt in sorted({n for n in (8, 16, 32, 64, threads) if n <= threads}):
-        torch.set_num_threads(nt)
-        o.llm_forward(e1, c1)
+    Sample per step (full widths, fp32): SAMPLE_FRAMES frames through SAMPLE_VIT_BLOCKS CLIP blocks + the slot pool,
+    SAMPLE_LLM_LAYERS decoder layers of prefill at the real S, SAMPLE_DECODE_TOKENS decode tokens through the same layers at
+    the real context, and one evaluation of the text head.  Depth, frames and tokens are then scaled linearly to the full
+    model (the reference is serial batch 1: `eval.sh:56`); the factors are printed in `sample`.  The oracle object and its
+    weights are built once; the thread count is chosen PER STAGE on the first step (torch's intra-op pool degrades when
+    oversubscribed on many-core boxes, differently for the GEMM-shaped and the GEMV-shaped stages)."""
+    SAMPLE_FRAMES = 16
+    SAMPLE_VIT_BLOCKS = 2
+    SAMPLE_LLM_LAYERS = 2
+    SAMPLE_DECODE_TOKENS = 8
+
+    def __init__(self, T, max_new, max_threads):
+        import dataclasses
+        from oracle import trace_oracle as orc
+        from trace_b200 import synth
+        self.T, self.max_new, self.max_threads = T, max_new, max_threads
+        self.full = synth.full_dims(T)
+        d = dataclasses.replace(self.full, vit_layers=self.SAMPLE_VIT_BLOCKS + 1, layers=self.SAMPLE_LLM_LAYERS)
+        sd = {}
+        for name, shape, kind in synth.param_specs(d):
+            if name == "model.embed_tokens.weight":
+                sd[name] = torch.zeros(shape)                      # gathers only; no need to randomise 131M values
+            else:
+                sd[name] = synth.synth_tensor(name, shape, kind, 0).float()
+        self.d = d
+        self.o = orc.TraceOracle(d, sd)
+        self.px, _ = synth.synthetic_clip(d, self.SAMPLE_FRAMES)
+        self.S = 14 * T + L_TEXT - 1
+        self.e = torch.randn(self.S, d.hidden) * 0.02
+        self.threads = None
+
+    def _pick(self, fn):
+        best = (1e30, self.max_threads)
+        for nt in sorted({n for n in (8, 16, 32, 64, self.max_threads) if n <= self.max_threads}):
+            torch.set_num_threads(nt)
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if dt < best[0]:
+                best = (dt, nt)
+        return best[1]
+
+    def calibrate(self):
+        o, d = self.o, self.d
+        _, c1 = o.llm_forward(self.e[:64], None)
+        self.threads = {
+            "vit": self._pick(lambda: o.vit_features(self.px[:2].float())),
+            "prefill": self._pick(lambda: o.llm_forward(self.e[:256], None)),
+            "decode": self._pick(lambda: o.llm_forward(self.e[:1], c1)),
+        }
+
+    def sample(self):
+        if self.threads is None:
+            self.calibrate()
+        o, full = self.o, self.full
+        T, max_new = self.T, self.max_new
+        torch.set_num_threads(self.threads["vit"])
         t0 = time.perf_counter()
-        for _ in range(3):
-            o.llm_forward(e1, c1)
-        dt = (time.perf_counter() - t0) / 3
-        if dt < best[0]:
-            best = (dt, nt)
-    threads = best[1]
-    torch.set_num_threads(threads)
-    t0 = time.perf_counter()
-    feats = o.vit_features(px.float())
-    t_vit_block_2f = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    o.slot_pool(feats)
-    t_proj_2f = time.perf_counter() - t0
-    S = 14 * T + L_TEXT - 1
-    e = torch.randn(S, d.hidden) * 0.02
-    t0 = time.perf_counter()
-    h, cache = o.llm_forward(e, None)
-    t_prefill_layer = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    for _ in range(4):
-        h1, cache = o.llm_forward(e[:1], cache)
-    t_decode_layer_tok = (time.perf_counter() - t0) / 4
-    t0 = time.perf_counter()
-    o.head_logits(h1[-1], 0)
-    t_head = time.perf_counter() - t0
-    vit = t_vit_block_2f * (full.vit_layers - 1) * (T / 2)
-    proj = t_proj_2f * (T / 2)
-    prefill = t_prefill_layer * full.layers
-    decode = (t_decode_layer_tok * full.layers) * max_new + t_head * max_new * (23.0 / TOKENS_PER_EVENT)
-    total = vit + proj + prefill + decode
-    events = max_new / TOKENS_PER_EVENT
-    return {"value": events / total, "unit": "events/s", "cores": threads, "kind": "port",
-            "sample": (f"oracle port fp32, full widths: 2 frames x 1 CLIP block ({t_vit_block_2f:.2f}s) x{full.vit_layers - 1} blocks x{T // 2}; "
-                       f"1 decoder layer prefill S={S} ({t_prefill_layer:.2f}s) x{full.layers}; 4 decode tokens x 1 layer "
-                       f"({t_decode_layer_tok * 1e3:.1f} ms/token/layer) x{full.layers} x{max_new}; text head {t_head * 1e3:.0f} ms; "
-                       f"=> {total:.0f} s per {T}-frame clip ({vit:.0f} ViT + {prefill:.0f} prefill + {decode:.0f} decode)"),
-            "seconds_per_clip": total}
+        feats = o.vit_features(self.px.float())
+        t_vit = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o.slot_pool(feats)
+        t_proj = time.perf_counter() - t0
+        torch.set_num_threads(self.threads["prefill"])
+        t0 = time.perf_counter()
+        h, cache = o.llm_forward(self.e, None)
+        t_prefill = time.perf_counter() - t0
+        torch.set_num_threads(self.threads["decode"])
+        t0 = time.perf_counter()
+        for _ in range(self.SAMPLE_DECODE_TOKENS):
+            h1, cache = o.llm_forward(self.e[:1], cache)
+        t_tok = (time.perf_counter() - t0) / self.SAMPLE_DECODE_TOKENS
+        t0 = time.perf_counter()
+        o.head_logits(h1[-1], 0)
+        t_head = time.perf_counter() - t0
+        f_vit = (full.vit_layers - 1) / self.SAMPLE_VIT_BLOCKS * (T / self.SAMPLE_FRAMES)
+        f_llm = full.layers / self.SAMPLE_LLM_LAYERS
+        vit = t_vit * f_vit
+        proj = t_proj * (T / self.SAMPLE_FRAMES)
+        prefill = t_prefill * f_llm
+        decode = t_tok * f_llm * max_new + t_head * max_new * (23.0 / TOKENS_PER_EVENT)
+        total = vit + proj + prefill + decode
+        events = max_new / TOKENS_PER_EVENT
+        cores = max(self.threads.values())
+        return {"value": events / total, "unit": "events/s", "cores": cores, "kind": "port", "seconds_per_clip": total,
+                "sample_seconds": t_vit + t_proj + t_prefill + t_tok * self.SAMPLE_DECODE_TOKENS + t_head,
+                "sample": (f"oracle port fp32, full widths; threads per stage {self.threads}; "
+                           f"ViT: {self.SAMPLE_FRAMES} frames x {self.SAMPLE_VIT_BLOCKS} CLIP blocks = {t_vit:.2f} s, x{f_vit:.1f} "
+                           f"({full.vit_layers - 1} blocks, {T} frames) = {vit:.0f} s; slot pool {proj:.1f} s; "
+                           f"prefill: {self.SAMPLE_LLM_LAYERS} decoder layers at S={self.S} = {t_prefill:.2f} s, x{f_llm:.0f} = {prefill:.0f} s; "
+                           f"decode: {self.SAMPLE_DECODE_TOKENS} tokens x {self.SAMPLE_LLM_LAYERS} layers at context {self.S} = "
+                           f"{t_tok * 1e3:.1f} ms/token, x{f_llm:.0f} layers x{max_new} tokens + text head {t_head * 1e3:.0f} ms x"
+                           f"{max_new * 23 // TOKENS_PER_EVENT} steps = {decode:.0f} s; => {total:.0f} s per {T}-frame clip")}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    s = CpuSampler(args.frames, args.max_new, os.cpu_count() or 1)
+    s.calibrate()
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(args.frames, args.max_new, threads)
+        r = s.sample()
         if i >= args.warmup:
             vals.append(r)
-        if i == 0 and r["seconds_per_clip"] > 0 and args.warmup + args.steps > 2:
-            pass
     v = sum(x["value"] for x in vals) / len(vals)
-    ms = 1e3 * sum(x["seconds_per_clip"] for x in vals) / len(vals)
+    lo, hi = min(x["value"] for x in vals), max(x["value"] for x in vals)
     line = {"impl": "reference", "metric": "events/sec end-to-end, 128-frame clip", "value": v, "unit": "events/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(x["sample_seconds"] for x in vals) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config 2: one {args.frames}-frame 336px clip, DVC prompt L={L_TEXT}, greedy {args.max_new} new tokens "
-                                   f"(reference is serial batch-1: N GPUs do not apply)", "tokens_per_event": TOKENS_PER_EVENT},
-            "cpu_baseline": {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+                                   f"(reference is serial batch-1: N GPUs do not apply)", "tokens_per_event": TOKENS_PER_EVENT,
+                       "note": "each step times a bounded sample of the clip (ms_per_step) and scales it to the whole clip (value); "
+                               "seconds_per_clip is the scaled figure"},
+            "seconds_per_clip": sum(x["seconds_per_clip"] for x in vals) / len(vals),
+            "spread": {"min": lo, "max": hi, "rel": (hi - lo) / v if v else None},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -218,12 +262,20 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 leg
 # ------------------------------------------------------------------------------------------------
+def decode_bytes_per_step(d, B, t_avg, text_frac):
+    """Algorithmic bytes of one decode step: fp16 layer weights + the head rows actually read + K/V."""
+    layer_w = d.layers * ((d.heads + 2 * d.kv_heads) * d.head_dim * d.hidden + d.heads * d.head_dim * d.hidden + 3 * d.ffn * d.hidden) * 2
+    head_b = (d.vocab + 1) * d.hidden * 2 * text_frac + 26 * d.hidden * 2 * (1 - text_frac)
+    kv_b = B * d.layers * 2 * d.kv_heads * d.head_dim * 2 * (t_avg + 1)
+    return layer_w + head_b + kv_b
+
+
 def run_b200(args):
     import torch.distributed as dist
     from trace_b200 import synth
     from trace_b200.events import count_events
     from trace_b200.model import TraceMistralConfig, TraceMistralForCausalLM
-    from trace_b200.parallel import attach_group
+    from trace_b200.parallel import generate_sharded, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,8 +286,14 @@ def run_b200(args):
     T, max_new = args.frames, args.max_new
     d = synth.full_dims(T)
     S = 14 * T + L_TEXT - 1
-    model = TraceMistralForCausalLM(TraceMistralConfig(d), device=local, vit_chunk_frames=32, max_prefill_tokens=S,
-                                    max_ctx=S + max_new + 64, kv_pages=2 * ((S + max_new + 64 + 63) // 64))
+    T3, B3, B4 = 64, 8, 4                                 # config 3: 8 x 64-frame clips; config 4: 4 x 128-frame clips per GPU
+    S3 = 14 * T3 + L_TEXT - 1
+    batched = not args.skip_batched
+    ctx_len = S + max_new + 64
+    rows = max(B3, B4) if batched else 1
+    model = TraceMistralForCausalLM(TraceMistralConfig(d), device=local, vit_chunk_frames=32,
+                                    max_prefill_tokens=max(S, B3 * S3, B4 * S) if batched else S,
+                                    max_ctx=ctx_len, kv_pages=(rows + 1) * ((ctx_len + 63) // 64))
     t_load = time.perf_counter()
     cache = {}
 
@@ -254,42 +312,36 @@ def run_b200(args):
     model.engine.load_state_dict([])      # finalize (all tensors already loaded)
     torch.cuda.synchronize()
     t_load = time.perf_counter() - t_load
-    if world > 1:
-        attach_group(model)
-
-    ids_row = bench_prompt_ids(T)
-    assert len(ids_row) == L_TEXT, len(ids_row)
-    ids = torch.tensor([ids_row], dtype=torch.int64, device="cuda")
-    mask = torch.ones_like(ids)
-    # one clip per rank per step; under sharding every rank needs every clip of the step (all ranks encode a slice of each)
-    clips_host, stamps = [], []
-    for r in range(world):
-        px, ts = synth.synthetic_clip(d, T, seed=1234 + r)
-        clips_host.append(px.pin_memory())
-        stamps.append(ts)
-    clips_dev = [c.cuda() for c in clips_host]
-    h2d_bytes = sum(c.numel() * 2 for c in clips_host) + ids.numel() * 8
     eng = model.engine
+    group = dist.group.WORLD if world > 1 else None
+    text_frac = 23.0 / TOKENS_PER_EVENT if args.weights == "structured" else 1.0
 
-    def step(resident: bool):
-        """One clip per rank.  Sharded ViT: every rank encodes its frame range of all `world` clips, all-gather, then
-        decodes its own clip."""
-        srcs = clips_dev if resident else [c.cuda(non_blocking=True) for c in clips_host]
-        heads = [1]
+    def make_workload(n_clips, frames, task, seed0):
+        """n_clips clips of `frames` frames in pinned host memory.  Under sharding a rank keeps (and uploads) only its frame
+        range of every clip."""
+        ids_row = bench_prompt_ids(frames, task)
+        assert len(ids_row) == L_TEXT, len(ids_row)
+        ids = torch.tensor([ids_row] * n_clips, dtype=torch.int64, device="cuda")
+        lo, hi = shard_bounds(frames, world, rank) if world > 1 else (0, frames)
+        host, stamps = [], []
+        for c in range(n_clips):
+            px, ts = synth.synthetic_clip(d, frames, seed=seed0 + c)
+            host.append(px[lo:hi].contiguous().pin_memory())
+            stamps.append(ts)
+        dev = [c.cuda() for c in host]
+        return {"ids": ids, "host": host, "dev": dev, "stamps": stamps, "n": n_clips, "frames": frames,
+                "h2d": sum(c.numel() * 2 for c in host) + ids.numel() * 8}
+
+    def run_workload(wl, resident, new_tokens):
+        """The public call: generate (1 GPU) / generate_sharded (N GPUs).  Returns ids [n_clips, n] (host)."""
+        srcs = wl["dev"] if resident else [c.cuda(non_blocking=True) for c in wl["host"]]
+        heads = [1] * wl["n"]
         if world == 1:
-            out = model.generate(ids, attention_mask=mask, images_or_videos=[srcs[0]], modal_list=["video"], video_timestamps=[stamps[0]],
-                                 heads=heads, do_sample=False, temperature=0.0, max_new_tokens=max_new, use_cache=True, pad_token_id=2)
+            out = model.generate(wl["ids"], attention_mask=torch.ones_like(wl["ids"]), images_or_videos=srcs, modal_list=["video"] * wl["n"],
+                                 video_timestamps=wl["stamps"], heads=heads, do_sample=False, temperature=0.0, max_new_tokens=new_tokens,
+                                 use_cache=True, pad_token_id=2)
         else:
-            from trace_b200.parallel import encode_frames_sharded
-            from trace_b200.model.encoders import frame_time_ids
-            frames = torch.cat(srcs, 0)
-            slots = encode_frames_sharded(eng, frames, world, T, model.dist_group).view(world, T, 8, d.hidden)
-            tid = torch.tensor([frame_time_ids(stamps[rank])], dtype=torch.int32, device="cuda")
-            emb = eng.build_prefill(ids, slots[rank:rank + 1].contiguous(), tid)
-            kv = [eng.alloc_slot(S + max_new)]
-            eng.prefill(kv, emb)
-            out = eng.decode(kv, heads, max_new)
-            eng.free_slot(kv[0])
+            out = generate_sharded(model, wl["ids"], srcs, wl["stamps"], heads, new_tokens, group, pad_token_id=2, local_slices=True)
         ms, st = eng.last_decode_timing()
         return out.cpu(), ms, st
 
@@ -298,8 +350,22 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max_sum(tmax, tsum):
+        a = torch.tensor(tmax, dtype=torch.float64, device="cuda")
+        b = torch.tensor(tsum, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        return a.tolist(), b.tolist()
+
+    def my_rows(out):
+        """Rows of `out` this rank decoded (every rank returns all rows under generate_sharded)."""
+        return [out[i] for i in range(rank, out.shape[0], world)] if world > 1 else list(out)
+
+    # ---------------- headline: config 2, one clip per GPU per step ----------------
+    wl2 = make_workload(world, T, "dvc", 1234)
     for _ in range(args.warmup):
-        out, _, _ = step(True)
+        run_workload(wl2, True, max_new)
     launches0 = eng.launch_count
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -310,11 +376,12 @@ def run_b200(args):
     e0.record()
     dec_ms, dec_steps, n_tok, n_ev = 0.0, 0, 0, 0
     for _ in range(args.steps):
-        out, ms, st = step(True)
+        out, ms, st = run_workload(wl2, True, max_new)
         dec_ms += ms
         dec_steps += st
-        n_tok += out.shape[1]
-        n_ev += count_events(out[0].tolist(), d.vocab)
+        for row in my_rows(out):
+            n_tok += row.numel()
+            n_ev += count_events(row.tolist(), d.vocab)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -323,24 +390,56 @@ def run_b200(args):
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    n_ev_e2e = 0
-    d2h = 0
+    n_ev_e2e, d2h = 0, 0
     for _ in range(args.steps):
-        out, _, _ = step(False)
-        n_ev_e2e += count_events(out[0].tolist(), d.vocab)
-        d2h += out.numel() * 8
+        out, _, _ = run_workload(wl2, False, max_new)
+        for row in my_rows(out):
+            n_ev_e2e += count_events(row.tolist(), d.vocab)
+            d2h += row.numel() * 8
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.finish() if sampler else None
+    (ms_total, ms_e2e), (ev_total, ev_e2e, tok_total) = reduce_max_sum([ms_total, ms_e2e], [n_ev, n_ev_e2e, n_tok])
+    hbm_peak, tf_peak, peak_src = peaks()
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([n_ev, n_ev_e2e, n_tok], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
-    ev_total, ev_e2e, tok_total = float(cnt[0]), float(cnt[1]), float(cnt[2])
+    # ---------------- batched configurations (their own sub-records; not part of `value`) ----------------
+    def batched_record(name, wl, B_local, desc):
+        run_workload(wl, True, max_new)                                   # warm-up (graph of this batch size, allocator)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out, ms, st = run_workload(wl, False, max_new)                    # end to end from pinned host memory
+        b.record()
+        barrier()
+        rows_ = my_rows(out)
+        ev = sum(count_events(r.tolist(), d.vocab) for r in rows_)
+        tok = sum(r.numel() for r in rows_)
+        (ms_run, ms_dec), (ev, tok) = reduce_max_sum([a.elapsed_time(b), ms], [ev, tok])
+        Sx = 14 * wl["frames"] + L_TEXT - 1
+        step_ms = ms_dec / max(st, 1)
+        bytes_step = decode_bytes_per_step(d, B_local, Sx + max_new / 2, text_frac)
+        ach = bytes_step / (step_ms * 1e-3) / 1e9
+        return {"workload": desc, "clips": wl["n"], "rows_per_decode_step": B_local, "value": ev / (ms_run * 1e-3), "unit": "events/s",
+                "measured": "end to end from pinned host memory through the public call, device time (CUDA events), max over ranks",
+                "ms": ms_run, "tokens_per_s": tok / (ms_run * 1e-3), "events_parsed": ev, "h2d_bytes": wl["h2d"],
+                "roofline": {"bound": "hbm", "kernel": f"decode_stream_kernel<{B_local}> (one launch per generated token per row batch)",
+                             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "bytes_per_step": bytes_step,
+                             "ms_per_decode_step": step_ms, "traffic": None}}
+
+    batched_out = {}
+    if batched:
+        if world == 1:
+            wl3 = make_workload(B3, T3, "mr", 4321)
+            batched_out["config3"] = batched_record("config3", wl3, B3, f"config 3: 1 GPU, batch of {B3} x {T3}-frame clips, moment-retrieval prompt "
+                                                    f"(S={S3}), greedy {max_new} new tokens per row")
+            del wl3
+        wl4 = make_workload(B4 * world, T, "dvc", 8765)
+        batched_out["config4"] = batched_record(
+            "config4", wl4, B4, (f"config 4 per GPU: {B4} x {T}-frame clips per GPU ({B4 * world} clips on {world} GPU(s)); "
+                                 + ("ViT on one GPU" if world == 1 else f"ViT frame-sharded {T // world} frames/GPU/clip + one all-gather of the slot tokens")
+                                 + f"; S={S}, greedy {max_new} new tokens per row"))
+        del wl4
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,27 +458,23 @@ def run_b200(args):
         return a.elapsed_time(b) / reps
 
     from trace_b200.model.encoders import frame_time_ids
-    ms_vit = timed(lambda: eng.encode_frames(clips_dev[0]))
-    slots0 = eng.encode_frames(clips_dev[0]).view(1, T, 8, d.hidden)
-    tid0 = torch.tensor([frame_time_ids(stamps[0])], dtype=torch.int32, device="cuda")
+    full_clip, stamps0 = synth.synthetic_clip(d, T, seed=1234)
+    full_clip = full_clip.cuda()
+    ms_vit = timed(lambda: eng.encode_frames(full_clip))
+    slots0 = eng.encode_frames(full_clip).view(1, T, 8, d.hidden)
+    tid0 = torch.tensor([frame_time_ids(stamps0)], dtype=torch.int32, device="cuda")
+    ids1 = wl2["ids"][:1].contiguous()
 
     def prefill_once():
-        emb = eng.build_prefill(ids, slots0, tid0)
+        emb = eng.build_prefill(ids1, slots0, tid0)
         kv = [eng.alloc_slot(S + 8)]
         eng.prefill(kv, emb)
         eng.free_slot(kv[0])
 
     ms_prefill = timed(prefill_once)
-    hbm_peak, tf_peak, peak_src = peaks()
     vit_flop = 366.0e9 * T                                          # 23 of 24 blocks + patch embed
     prefill_flop = 2 * 6.979e9 * S + 262144.0 * S * S
-    # algorithmic bytes of one decode step at B=1: fp16 layer weights + head actually read + KV
-    layer_w = d.layers * ((d.heads + 2 * d.kv_heads) * d.head_dim * d.hidden + d.heads * d.head_dim * d.hidden + 3 * d.ffn * d.hidden) * 2
-    text_frac = 23.0 / TOKENS_PER_EVENT if args.weights == "structured" else 1.0
-    head_b = (d.vocab + 1) * d.hidden * 2 * text_frac + 26 * d.hidden * 2 * (1 - text_frac)
-    t_avg = S + max_new / 2
-    kv_b = d.layers * 2 * d.kv_heads * d.head_dim * 2 * (t_avg + 1)
-    bytes_step = layer_w + head_b + kv_b
+    bytes_step = decode_bytes_per_step(d, 1, S + max_new / 2, text_frac)
     step_ms = dec_ms / max(dec_steps, 1)
     achieved = bytes_step / (step_ms * 1e-3) / 1e9
     value = ev_total / (ms_total * 1e-3)
@@ -391,19 +486,21 @@ def run_b200(args):
                                 f"Mistral-7B, llama_2+dvc prompt L={L_TEXT} (S={S}), greedy {max_new} new tokens, heads=[1]"),
                    "clips_per_step": world, "frames": T, "prompt_len": L_TEXT, "prefill_len": S, "max_new_tokens": max_new,
                    "weights": args.weights + " synthetic fp16 (seed 0)", "tokens_per_event": TOKENS_PER_EVENT,
-                   "decode_path": "per-op kernels + CUDA graph" if os.environ.get("TRACE_B200_DECODE_PEROP") == "1" else "fused persistent decode-step kernel, 1 launch/token (CUDA graph)",
+                   "api": "TraceMistralForCausalLM.generate" if world == 1 else "trace_b200.parallel.generate_sharded (local frame slices)",
+                   "decode_path": ("round-1 fused decode kernel" if os.environ.get("TRACE_B200_DECODE") == "1" else
+                                   "streamed decode step: one cooperative kernel per token (CUDA graph), weights + K/V pages through one TMA ring"),
                    "parallelism": "1 GPU" if world == 1 else f"frame-sharded ViT x{world} + 1 all-gather, replicated LLM, 1 clip/GPU",
                    "l2_policy": "per-step working set (14.5 GB weights) >> 126 MB L2, no flush needed",
                    "weight_init_s": round(t_load, 1)},
         "events_parsed": ev_total, "tokens_generated": tok_total, "tokens_per_s": tok_total / (ms_total * 1e-3),
         "nominal_events_per_s": tok_total / TOKENS_PER_EVENT / (ms_total * 1e-3),
         "gpu_launches": int(launches),
-        "e2e": {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h // args.steps,
+        "e2e": {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": wl2["h2d"], "d2h_bytes_per_step": int(d2h) // args.steps,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": {"bound": "hbm", "kernel": "decode_step_kernel (one launch per generated token: 32 layers + heads + argmax/head-switch)",
+        "roofline": {"bound": "hbm", "kernel": "decode_stream_kernel<1> (one launch per generated token: 32 layers + heads + argmax/head-switch)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE, "bytes_per_step": bytes_step, "ms_per_decode_step": step_ms,
-                     "decode_share_of_step": dec_ms / ms_total},
+                     "traffic": NCU_DRAM["bytes"], "traffic_source": NCU_DRAM["source"], "bytes_per_step": bytes_step, "ms_per_decode_step": step_ms,
+                     "decode_share_of_step": dec_ms / (ms_total if world == 1 else max(ms_total, 1e-9))},
         "stages": {
             "vit_encode": {"ms": ms_vit, "tflops": vit_flop / (ms_vit * 1e-3) / 1e12, "frac_of_tensor_peak": vit_flop / (ms_vit * 1e-3) / 1e12 / tf_peak,
                            "tensor_peak_tflops": tf_peak, "flop": vit_flop, "note": "CLIP-ViT-L/14-336 x%d frames + slot pool, tcgen05 GEMMs; tensor-pipe %% per kernel from ncu in profiles/" % T},
@@ -411,11 +508,15 @@ def run_b200(args):
                         "frac_of_tensor_peak": prefill_flop / (ms_prefill * 1e-3) / 1e12 / tf_peak, "flop": prefill_flop, "tokens": S},
             "decode": {"ms_per_token": step_ms, "tokens": max_new},
         },
+        "batched": batched_out,
         "clocks": clocks,
     }
     if not args.skip_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = {k: v for k, v in cpu_sample(T, max_new, os.cpu_count() or 1).items() if k != "seconds_per_clip"}
+            cs = CpuSampler(T, max_new, os.cpu_count() or 1)
+            r = cs.sample()
+            line["cpu_baseline"] = {k: v for k, v in r.items() if k not in ("seconds_per_clip", "sample_seconds")}
+            line["cpu_baseline"]["seconds_per_clip"] = r["seconds_per_clip"]
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
     print(json.dumps(line))

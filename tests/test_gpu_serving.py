@@ -196,3 +196,46 @@ def test_forward_full_sequence_logits(use_heads):
             assert float((got[fin] - want[fin]).abs().max()) < LOGIT_TOL, f"row {b} pos {pos}: {float((got[fin] - want[fin]).abs().max())}"
     with pytest.raises(NotImplementedError):
         model.forward(ids, labels=ids)
+
+
+def test_safetensors_checkpoint_loads_and_generates(tmp_path):
+    """load_pretrained_model on a real checkpoint directory (config.json + sharded *.safetensors with the HF names, the CLIP
+    tower in its own `mm_vision_tower` directory as the released checkpoints have it, trace_arch.py:34-36) -> packed engine
+    layout (fused QKV, interleaved gate/up, stacked heads) -> generate: ids must equal the reference's golden ids."""
+    import json
+    from safetensors.torch import save_file
+    from tests.util import load_case, compare_ids_with_margin
+    from trace_b200.model.builder import load_pretrained_model
+    c = load_case("tiny_b1")
+    d, meta, z = c["dims"], c["meta"], c["z"]
+    sd = synth.make_state_dict(d, meta["seed"])
+    vt = "model.vision_tower.vision_tower."
+    clip_dir = tmp_path / "clip-vit-synth"
+    clip_dir.mkdir()
+    # the tower's own checkpoint: HF CLIPVisionModel names ("vision_model....")
+    save_file({k[len(vt):]: v.contiguous() for k, v in sd.items() if k.startswith(vt)}, str(clip_dir / "model.safetensors"))
+    json.dump({"hidden_size": d.vit_width, "num_attention_heads": d.vit_heads, "num_hidden_layers": d.vit_layers, "intermediate_size": d.vit_mlp,
+               "image_size": d.image_size, "patch_size": d.patch_size, "layer_norm_eps": d.vit_ln_eps}, open(clip_dir / "config.json", "w"))
+    ck = tmp_path / "trace-synth"
+    ck.mkdir()
+    rest = {k: v.contiguous() for k, v in sd.items() if not k.startswith(vt)}
+    names = sorted(rest)
+    half = len(names) // 2
+    save_file({k: rest[k] for k in names[:half]}, str(ck / "model-00001-of-00002.safetensors"))
+    save_file({k: rest[k] for k in names[half:]}, str(ck / "model-00002-of-00002.safetensors"))
+    json.dump({"architectures": ["TraceMistralForCausalLM"], "model_type": "trace_mistral", "hidden_size": d.hidden, "intermediate_size": d.ffn,
+               "num_hidden_layers": d.layers, "num_attention_heads": d.heads, "num_key_value_heads": d.kv_heads, "vocab_size": d.vocab,
+               "rms_norm_eps": d.rms_eps, "rope_theta": d.rope_theta, "mm_vision_tower": str(clip_dir), "mm_projector_type": "spatial_slot",
+               "num_frames": meta["T"], "image_aspect_ratio": "pad"}, open(ck / "config.json", "w"))
+    tokenizer, model, processor, context_len = load_pretrained_model(str(ck), None, "trace-synth", vit_chunk_frames=4, max_prefill_tokens=1024,
+                                                                     max_ctx=512)
+    assert context_len == 2048 and processor is model.get_vision_tower().image_processor
+    ids = torch.tensor(c["prompt_ids"], dtype=torch.int64, device="cuda")
+    out = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=[c["clips"][0].cuda()], modal_list=["video"],
+                         video_timestamps=c["ts"], heads=[1], do_sample=False, max_new_tokens=meta["max_new"], pad_token_id=2)
+    n, ties = compare_ids_with_margin(out.cpu().tolist(), z["out_ids"].tolist(), z["top_vals"], LOGIT_TOL, "safetensors checkpoint")
+    assert n > 0
+    # a second generate on the SAME model with another budget and sampling switched on and off again (decode graph reuse)
+    out2 = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=[c["clips"][0].cuda()], modal_list=["video"],
+                          video_timestamps=c["ts"], heads=[1], do_sample=False, max_new_tokens=7, pad_token_id=2)
+    assert torch.equal(out2, out[:, :7])

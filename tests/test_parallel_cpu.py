@@ -61,11 +61,12 @@ class _FakeModel:
         self.generation_config = types.SimpleNamespace(eos_token_id=2, pad_token_id=None)
         self.calls = []
 
-    def _encode_slots(self, clips):
+    def _encode_slots(self, clips, presliced_T=None):
         from trace_b200.parallel import encode_frames_sharded
-        B, T = len(clips), clips[0].shape[0]
+        B, T = len(clips), clips[0].shape[0] if presliced_T is None else presliced_T
         frames = torch.cat(clips, 0)
-        out = encode_frames_sharded(_FakeEngine(), frames, B, T, self.dist_group) if self.dist_group is not None else _FakeEngine().encode_frames(frames)
+        out = (encode_frames_sharded(_FakeEngine(), frames, B, T, self.dist_group, presliced=presliced_T is not None)
+               if self.dist_group is not None else _FakeEngine().encode_frames(frames))
         return out.view(B, T, 8, -1)
 
     def _generate_from_slots(self, ids, slots, tid, heads, max_new, eos, pad):
@@ -101,6 +102,12 @@ def _worker_generate(rank, world, port, q):
     n = out.shape[1]
     ok = torch.equal(out, ref[:, :n]) and bool((ref[:, n:] == 9).all()) and heads == ref_heads
     ok = ok and m.calls == [len(clips_of_rank(B, world, rank))]
+    # the same call with every rank holding only ITS frames of every clip (what a loader that reads from the host uploads)
+    from trace_b200.parallel import shard_bounds
+    lo, hi = shard_bounds(T, world, rank)
+    heads2 = [1] * B
+    out2 = generate_sharded(_FakeModel(), ids, [c[lo:hi] for c in clips], ts, heads2, 6, dist.group.WORLD, pad_token_id=9, local_slices=True)
+    ok = ok and torch.equal(out2, out) and heads2 == heads
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

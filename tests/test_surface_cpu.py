@@ -251,3 +251,60 @@ def test_load_pretrained_model_safetensors_branch(tmp_path, monkeypatch):
         builder.load_pretrained_model(str(tmp_path), None, "trace-lora")
     with pytest.raises(NotImplementedError):
         builder.load_pretrained_model(str(tmp_path), None, "trace", load_4bit=True)
+
+
+def test_load_pretrained_model_clip_tower_from_mm_vision_tower_dir(tmp_path, monkeypatch):
+    """Released checkpoints keep the frozen CLIP tower out of the LLM shards: it is loaded from the directory
+    `config.mm_vision_tower` names (trace_arch.py:34-36, clip_encoder.py:23-29), whose own config.json carries the ViT geometry."""
+    import json
+    import torch
+    from safetensors.torch import save_file
+    from trace_b200.model import builder
+
+    d = synth.tiny_dims(4)
+    sd = synth.make_state_dict(d, 0)
+    vt = "model.vision_tower.vision_tower."
+    clip = tmp_path / "clip-vit-synth"
+    clip.mkdir()
+    tower = {k[len(vt):]: v.contiguous() for k, v in sd.items() if k.startswith(vt)}
+    tower["text_model.embeddings.token_embedding.weight"] = torch.zeros(4, 4)       # a full CLIPModel export: ignored
+    save_file(tower, str(clip / "model.safetensors"))
+    (clip / "config.json").write_text(json.dumps({"vision_config": {
+        "hidden_size": d.vit_width, "num_attention_heads": d.vit_heads, "num_hidden_layers": d.vit_layers, "intermediate_size": d.vit_mlp,
+        "image_size": d.image_size, "patch_size": d.patch_size}}))
+    ck = tmp_path / "trace"
+    ck.mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items() if not k.startswith(vt)}, str(ck / "model.safetensors"))
+    cfg = {"hidden_size": d.hidden, "num_hidden_layers": d.layers, "num_attention_heads": d.heads, "num_key_value_heads": d.kv_heads,
+           "intermediate_size": d.ffn, "vocab_size": d.vocab, "mm_vision_tower": str(clip)}
+    (ck / "config.json").write_text(json.dumps(cfg))
+
+    class FakeEngine:
+        def __init__(self):
+            self.loaded = {}
+
+        def load_weight(self, name, t):
+            self.loaded[name] = t
+
+        def load_state_dict(self, items):
+            pass
+
+    class FakeModel:
+        def __init__(self, config, device=0, **kw):
+            self.config, self.engine = config, FakeEngine()
+
+        def get_vision_tower(self):
+            import types
+            return types.SimpleNamespace(image_processor="processor")
+
+    monkeypatch.setattr(builder, "TraceMistralForCausalLM", FakeModel)
+    _, model, _, _ = builder.load_pretrained_model(str(ck), None, "trace")
+    assert sorted(model.engine.loaded) == sorted(sd)                               # tower tensors under the state-dict prefix, nothing else
+    assert (model.config.dims.vit_width, model.config.dims.image_size, model.config.dims.vit_layers) == (d.vit_width, d.image_size, d.vit_layers)
+    k = vt + "vision_model.encoder.layers.0.mlp.fc1.weight"
+    assert torch.equal(model.engine.loaded[k], sd[k])
+    # a tower that cannot be found is a loud error, not random weights
+    cfg["mm_vision_tower"] = "openai/clip-vit-large-patch14-336"
+    (ck / "config.json").write_text(json.dumps(cfg))
+    with pytest.raises(FileNotFoundError):
+        builder.load_pretrained_model(str(ck), None, "trace")

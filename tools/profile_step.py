@@ -38,6 +38,10 @@ model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frame
 for name, shape, kind in synth.param_specs(d):
     model.engine.load_weight(name, synth.synth_tensor(name, shape, kind, 0, device="cuda"))
 model.engine.load_state_dict([])
+sh = model.engine.sm_shares()
+if sh:
+    srt = sorted(sh)
+    print(f"SM bandwidth shares (relative to uniform): min {srt[0]:.3f} p10 {srt[len(srt) // 10]:.3f} median {srt[len(srt) // 2]:.3f} p90 {srt[9 * len(srt) // 10]:.3f} max {srt[-1]:.3f}")
 ids = torch.tensor([bench_prompt_ids(a.frames)] * a.batch, dtype=torch.int64, device="cuda")
 clips, stamps = [], []
 for b in range(a.batch):
@@ -52,25 +56,43 @@ torch.cuda.synchronize()
 ms, st = model.engine.last_decode_timing()
 import hashlib
 print("ids", out.tolist()[0][:16], "sha", hashlib.sha1(str(out.tolist()).encode()).hexdigest()[:12])
-if os.environ.get("TRACE_B200_MEGA_TIMING"):
+if os.environ.get("TRACE_B200_MEGA_TIMING") and os.environ.get("TRACE_B200_DECODE") == "1":
+    pass   # the round-1 kernel's stamp layout is no longer decoded here
+elif os.environ.get("TRACE_B200_MEGA_TIMING"):
+    # decode_stream.cu stamps per layer: 10+2*type staged, 24+type consumed, 11+2*type epilogue written (type 0 qkv, 1 o, 2 gate/up,
+    # 3 down); attention: 20 q ready, 21 K/V tiles done, 22 partials written, 23 combine written, 3 phase left
     tl = model.engine.debug_timeline().double() / 1e3   # us
-    names = ["qkv", "sync1", "attn", "sync2", "o", "sync3", "gateup", "sync4", "down"]
     for c in range(2):
-        x = tl[c, 1:-1]
-        d = x[:, 1:10] - x[:, 0:9]
-        nxt = tl[c, 2:, 0] - tl[c, 1:-1, 9]
-        print(f"cta{c}: " + " ".join(f"{n}={float(d[:, i].mean()):.2f}" for i, n in enumerate(names)) + f" sync0={float(nxt.mean()):.2f} layer={float((tl[c, 2:, 0] - tl[c, 1:-1, 0]).mean()):.2f} us")
-        for nm, st0, k in (("qkv", 0, 10), ("o", 4, 12), ("gateup", 6, 14), ("down", 8, 16)):
-            print(f"   {nm}: stage_x={float((x[:, k] - x[:, st0]).mean()):.2f} consume={float((x[:, k + 1] - x[:, k]).mean()):.2f} epilogue={float((x[:, st0 + 1] - x[:, k + 1]).mean()):.2f}")
-if os.environ.get("TRACE_B200_MEGA_TIMING"):
-    for c in range(2):
-        x = tl[c, 1:-1]
-        pts = [x[:, 2], x[:, 20], x[:, 21], x[:, 22], x[:, 23], x[:, 24], x[:, 3]]
-        nm = ["q+rope", "K/V+scores", "softmax", "PV+reduce", "partials+atomic", "merge(last)"]
-        print(f"   cta{c} attn: " + " ".join(f"{n}={float((pts[i + 1] - pts[i]).mean()):.2f}" for i, n in enumerate(nm)))
-if os.environ.get("TRACE_B200_MEGA_TIMING"):
-    raw = model.engine.debug_timeline()
-    for c in range(2):
-        print(f"   cta{c} stages parked in TMEM at phase start: " + " ".join(
-            f"{n}={float(raw[c, 1:-1, 25 + i].double().mean()):.2f}" for i, n in enumerate(["qkv", "o", "gateup", "down"])))
+        x = tl[c, 1:-1]            # layers 1 .. L-2 (layer 0 follows the prologue, the last one is overwritten by the head phase)
+        prev_dn = tl[c, 0:-2, 17]
+        seg = [("qkv.wait_x", prev_dn, x[:, 10]), ("qkv.stream", x[:, 10], x[:, 24]), ("qkv.epi", x[:, 24], x[:, 11]),
+               ("attn.wait_q", x[:, 11], x[:, 20]), ("attn.tiles", x[:, 20], x[:, 21]), ("attn.merge", x[:, 21], x[:, 22]),
+               ("attn.combine", x[:, 22], x[:, 23]), ("o.wait_attn", x[:, 23], x[:, 12]), ("o.stream", x[:, 12], x[:, 25]),
+               ("o.epi", x[:, 25], x[:, 13]), ("gu.wait_x", x[:, 13], x[:, 14]), ("gu.stream", x[:, 14], x[:, 26]),
+               ("gu.epi", x[:, 26], x[:, 15]), ("dn.wait_act", x[:, 15], x[:, 16]), ("dn.stream", x[:, 16], x[:, 27]),
+               ("dn.epi", x[:, 27], x[:, 17])]
+        tot = float((x[:, 17] - prev_dn).mean())
+        print(f"cta{c}: layer={tot:.2f} us | " + " ".join(f"{n}={float((b - a_).mean()):.2f}" for n, a_, b in seg))
+        stream = sum(float((b - a_).mean()) for n, a_, b in seg if n.endswith(".stream"))
+        wait = sum(float((b - a_).mean()) for n, a_, b in seg if ".wait" in n)
+        print(f"   cta{c}: streaming {stream:.2f} us, exchange waits {wait:.2f} us, attention compute {float((x[:, 23] - x[:, 20]).mean()):.2f} us, "
+              f"epilogues {sum(float((b - a_).mean()) for n, a_, b in seg if n.endswith('.epi')):.2f} us")
+if os.environ.get("TRACE_B200_MEGA_TIMING") and os.environ.get("TRACE_B200_DECODE") != "1":
+    _, pc = model.engine.debug_timeline(per_cta=True)
+    pc = pc.double()
+    import json as _json
+    rec = {"smid": pc[:, 31].long().tolist()}
+    t0 = float(pc[:, 10].min())
+    for nm, k in (("qkv_staged", 10), ("qkv_done", 24), ("o_staged", 12), ("o_done", 25), ("gu_staged", 14), ("gu_done", 26),
+                  ("dn_staged", 16), ("dn_done", 27)):
+        rec[nm] = [round((float(v) - t0) / 1e3, 3) for v in pc[:, k]]
+    for a_, b_ in (("gu_staged", "gu_done"), ("dn_staged", "dn_done")):
+        dur = [y - x for x, y in zip(rec[a_], rec[b_])]
+        srt = sorted(dur)
+        print(f"per-CTA {a_}->{b_}: min {srt[0]:.2f} p10 {srt[len(srt) // 10]:.2f} median {srt[len(srt) // 2]:.2f} p90 {srt[9 * len(srt) // 10]:.2f} max {srt[-1]:.2f} us")
+    for nm in ("gu_done", "dn_done", "qkv_done", "o_done"):
+        srt = sorted(rec[nm])
+        print(f"per-CTA {nm} finish spread: first {srt[0]:.2f} median {srt[len(srt) // 2]:.2f} p90 {srt[9 * len(srt) // 10]:.2f} last {srt[-1]:.2f} us")
+    os.makedirs("gpurun_out", exist_ok=True)
+    _json.dump(rec, open(f"gpurun_out/per_cta_{os.environ.get('AB_NAME', 'run')}.json", "w"))
 print(f"DECODE_TIMING ms={ms:.2f} passes={st} ms_per_step={ms / max(st - 1, 1):.4f} box_copy_GBs={BOX_GBS:.0f} floor_ms_at_box_bw={14.0e9 / BOX_GBS / 1e6:.3f}")

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 GPU session 5: bandwidth-balanced row partition + dense exchange at batch >= 4 -- parity, then timelines.
+mkdir -p gpurun_out
+run() { local n=$1 t=$2; shift 2; timeout $t "$@" > gpurun_out/$n.log 2>&1; echo "$n exit $? | $(tail -1 gpurun_out/$n.log | cut -c1-300)"; }
+run smoke 240 python __graft_entry__.py smoke
+grep -q "smoke ok" gpurun_out/smoke.log || { tail -5 gpurun_out/smoke.log; exit 1; }
+run test_gpu_wide 900 python -m pytest tests/test_gpu_wide.py -m gpu -q -x --timeout 400 -p no:cacheprovider -s
+grep -E "FAILED|Error|assert|worst|graph loop|watchdog" gpurun_out/test_gpu_wide.log | head -12
+run test_gpu_e2e 600 python -m pytest tests/test_gpu_e2e.py -m gpu -q -x --timeout 400 -p no:cacheprovider
+run test_gpu_serving 900 python -m pytest tests/test_gpu_serving.py tests/test_gpu_sampling.py -m gpu -q --timeout 400 -p no:cacheprovider
+grep -E "FAILED|Error|assert" gpurun_out/test_gpu_serving.log | head -12
+export TRACE_B200_MEGA_TIMING=1 MAXNEW=64
+bash tools/ab.sh bal: nobal:TRACE_B200_BALANCE=0
+BATCH=4 bash tools/ab.sh b4:
+BATCH=8 bash tools/ab.sh b8:

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 GPU session 6: closed-loop balance, batch-4/8 staging changes, warp-per-row norms, tensor-map cache -- whole GPU suite,
+# then timelines at batch 1 / 4 / 8 and the bench line.
+mkdir -p gpurun_out
+run() { local n=$1 t=$2; shift 2; timeout $t "$@" > gpurun_out/$n.log 2>&1; echo "$n exit $? | $(tail -1 gpurun_out/$n.log | cut -c1-300)"; }
+run smoke 240 python __graft_entry__.py smoke
+grep -q "smoke ok" gpurun_out/smoke.log || { tail -5 gpurun_out/smoke.log; exit 1; }
+run test_gpu_all 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider
+grep -E "FAILED|Error|assert" gpurun_out/test_gpu_all.log | head -20
+export TRACE_B200_MEGA_TIMING=1 MAXNEW=192
+bash tools/ab.sh bal:
+MAXNEW=160 BATCH=4 bash tools/ab.sh b4:
+MAXNEW=160 BATCH=8 bash tools/ab.sh b8:
+unset TRACE_B200_MEGA_TIMING
+timeout 900 python bench.py --steps 2 --warmup 2 --skip-cpu-baseline > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit $?"
+tail -3 gpurun_out/bench_full.err
+python - <<'PY'
+import json
+j = json.loads([l for l in open("gpurun_out/bench_full.json").read().strip().splitlines() if l.startswith("{")][-1])
+print("events/s", round(j["value"], 3), "e2e", round(j["e2e"]["value"], 3), "ms/decode", round(j["roofline"]["ms_per_decode_step"], 4), "frac", round(j["roofline"]["frac"], 3),
+      "vit ms", round(j["stages"]["vit_encode"]["ms"], 2), "prefill ms", round(j["stages"]["prefill"]["ms"], 2))
+for k, v in j.get("batched", {}).items():
+    print(k, "events/s", round(v["value"], 2), "ms", round(v["ms"], 1), "ms/step", round(v["roofline"]["ms_per_decode_step"], 3), "frac", round(v["roofline"]["frac"], 3))
+PY

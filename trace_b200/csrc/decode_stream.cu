@@ -21,6 +21,8 @@
 //
 // Replaces: trace_mistral.py:114-264 forward (decoder layers via HF MistralModel, heads :190-200, mask :244-252),
 // :336-344 head switch, trace_arch.py:345-375 embedding dispatch, HF greedy / sampling step -- for one generated token.
+#include <vector>
+
 #include "common.cuh"
 #include "decode_dev.cuh"
 #include "kernels.h"
@@ -35,8 +37,13 @@ constexpr int DS_MAX_LAYERS = 48;
 constexpr int DS_STAGE_HALVES = GV_TILE * (1024 + WS_PAD);     // 33792 B: 16 weight rows x 1024 columns, or one K|V page tile
 constexpr uint32_t DS_KV_TILE_BYTES = 2 * DS_PAGE * DS_HD * 2; // 32768
 constexpr unsigned DS_EPOCH_STRIDE = 512;                      // epochs reserved per launch (8 per layer + head)
-constexpr int DS_RES_PITCH = 32;                               // residual rows kept per CTA (H/148 -> <= 30)
-constexpr unsigned long long DS_TIMEOUT_NS = 4000000000ull;
+constexpr int DS_RES_PITCH = 40;                               // residual rows kept per CTA (H/148 = 27.7, + the bandwidth-share skew)
+// Block = 2 consumer warpgroups (8 warps) + 1 producer warpgroup (warp 8 streams, warps 9..11 only exist so that
+// setmaxnreg -- a warpgroup-wide instruction -- can move registers: 384 x 168 at launch -> consumers 224, producer group 56).
+// With 219 KB of the SM's 256 KB configured as shared memory the L1 is a few KB: a spilled register is an L2 round trip.
+constexpr int DS_THREADS = GV_CONS + 128;
+constexpr int DS_REGS_CONSUMER = 224;
+constexpr int DS_REGS_PRODUCER = 56;
 
 struct DsLayer {
   const __half *ln1, *qkv_w, *o_w, *ln2, *gateup_w, *down_w;
@@ -53,6 +60,9 @@ struct DsParams {
   __half* x_next;                       // dense [B,H]: next step's input embedding (same buffer as x)
   uint2 *x_ll, *qkv_ll, *attn_ll, *act_ll, *part_o_ll;
   uint4 *part_ml_ll, *cand_ll;
+  // batch >= 4: the large exchanges are plain fp16 buffers + one epoch flag per producer CTA (fx / fq / fa / fact: [gridDim] each)
+  __half *xd, *qkvd, *attnd, *actd;
+  unsigned *fx, *fq, *fa, *fact;
   const float *cos_tab, *sin_tab;
   const int32_t* block_table;
   int max_pages;
@@ -66,6 +76,10 @@ struct DsParams {
   int kp[5], ks[5];
   int part_bytes, stages, xs_cap, group_tiles;
   int advance;
+  const float* cum;                     // [gridDim+1] cumulative row share per SM id (null: uniform partition by blockIdx)
+  unsigned* stream_ns;                  // [gridDim] out: time this CTA spent in the four streaming phases of the step, by SM id
+  int watchdog_ms;                      // every wait in the kernel traps after this long (a protocol error must not hang the GPU)
+  int poll_sleep_ns;                    // back-off between re-polls of an exchange unit that has not arrived (0 = none)
   unsigned long long* dbg;
 };
 
@@ -85,8 +99,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 struct Watch {
-  unsigned long long t0;
+  unsigned long long t0, limit_ns;
   int* err;
+  unsigned sleep_ns;
 };
 __device__ __noinline__ void ds_die(int* err, int code) {
   atomicExch(err, code * 1000 + static_cast<int>(blockIdx.x));
@@ -94,7 +109,12 @@ __device__ __noinline__ void ds_die(int* err, int code) {
   __trap();
 }
 __device__ __forceinline__ void ds_watch(const Watch& w, unsigned& spins, int code) {
-  if ((++spins & 1023u) == 0 && gtimer() - w.t0 > DS_TIMEOUT_NS) ds_die(w.err, code);
+  if ((++spins & 1023u) == 0 && gtimer() - w.t0 > w.limit_ns) ds_die(w.err, code);
+}
+// between two polls of an exchange unit that has not arrived yet
+__device__ __forceinline__ void ds_repoll(const Watch& w, unsigned& spins, int code) {
+  ds_watch(w, spins, code);
+  if (w.sleep_ns) __nanosleep(w.sleep_ns);
 }
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -126,24 +146,47 @@ __device__ __forceinline__ uint4 ll_wait16(const void* p, unsigned epoch, const 
   uint4 v = ll_ld16(p);
   unsigned spins = 0;
   while (v.y != epoch || v.w != epoch) {
-    ds_watch(w, spins, code);
+    ds_repoll(w, spins, code);
     v = ll_ld16(p);
   }
   return v;
 }
 __device__ __forceinline__ uint32_t half_bits(float v) { return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(v))); }
 
-// Rows are dealt to the CTAs in units of `unit` (2: output pairs share one exchange unit; 4: two SwiGLU pairs do).
-__device__ __forceinline__ void ds_rows(int N, int unit, int& r0, int& r1) {
+// Rows are dealt to the CTAs in units of `unit` (2: output pairs share one exchange unit; 4: two SwiGLU pairs do).  A CTA is
+// identified by `vid`: blockIdx, or -- with the bandwidth-balanced partition -- the id of the SM it runs on.  Under HBM
+// saturation the SMs do not get equal shares of the bandwidth (+-5 %, a fixed property of each SM's position: measured,
+// profiles/r02_decode_timeline.md), so with equal row counts every phase ends with the whole grid waiting for the same few
+// SMs.  `cum` holds the cumulative share per SM id, rows are dealt proportionally, and the shares come from the kernel
+// itself: every launch reports the time each SM spent streaming (`stream_ns`), and the engine nudges the shares towards
+// equal times during the first decode bursts (engine.cu: rebalance).  The arithmetic of a row does not depend on which CTA
+// computes it, so results are bit-identical under any partition.
+__device__ __forceinline__ void rows_of_cta(const float* cum, int N, int unit, int c, int grid, int& r0, int& r1) {
   const long long U = N / unit;
-  r0 = static_cast<int>(U * blockIdx.x / gridDim.x) * unit;
-  r1 = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * unit;
-  if (blockIdx.x == gridDim.x - 1) r1 = N;
+  if (cum != nullptr) {
+    r0 = static_cast<int>(__float2ll_rn(static_cast<float>(U) * cum[c])) * unit;
+    r1 = (c == grid - 1) ? N : static_cast<int>(__float2ll_rn(static_cast<float>(U) * cum[c + 1])) * unit;
+  } else {
+    r0 = static_cast<int>(U * c / grid) * unit;
+    r1 = (c == grid - 1) ? N : static_cast<int>(U * (c + 1) / grid) * unit;
+  }
 }
 
+// timeline (TRACE_B200_MEGA_TIMING=1): [2 CTAs][layers][32] stamps of CTAs 0 and 77, then [gridDim][32] stamps of EVERY CTA for
+// the middle layer (slot 31 = %smid): how unevenly the SMs finish a phase
 __device__ __forceinline__ void stamp(const DsParams& p, int l, int k) {
-  if (p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
-    p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 32 + k] = gtimer();
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    const unsigned long long t = gtimer();
+    if (blockIdx.x == 0 || blockIdx.x == 77) p.dbg[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * p.layers + l) * 32 + k] = t;
+    if (l == p.layers / 2) {
+      unsigned long long* q = p.dbg + static_cast<size_t>(2) * p.layers * 32 + static_cast<size_t>(blockIdx.x) * 32;
+      q[k] = t;
+      if (k == 10) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        q[31] = smid;
+      }
+    }
   }
 }
 
@@ -173,11 +216,64 @@ __device__ __forceinline__ void stage_ll(__half* xs, int pitch, const uint2* src
         const int b = idx / per_row, j = idx - b * per_row;
         unsigned spins = 0;
         while (v[i].y != epoch || v[i].w != epoch) {
-          ds_watch(w, spins, 21);
+          ds_repoll(w, spins, 21);
           v[i] = ll_ld16(s4 + static_cast<size_t>(b) * row4 + j);
         }
         *reinterpret_cast<uint2*>(xs + static_cast<size_t>(b) * pitch + 4 * j) = make_uint2(v[i].x, v[i].z);
       }
+    }
+  }
+}
+
+// ---- dense exchange (batch >= 4) -----------------------------------------------------------------------------------
+// At batch 4..8 an activation vector is 32..460 KB per CTA per phase: doubling it with in-band flags and polling it unit by
+// unit costs more than it saves.  There the producers write plain fp16 and then release ONE epoch flag per CTA; consumers
+// acquire the flags of the CTAs they depend on (one poll per thread), then read the data with wide loads, all in flight.
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all 256 consumer threads, after the CTA's stores of the exchange (bar.sync + release: cumulative over the CTA's writes)
+__device__ __forceinline__ void publish(unsigned* flags, int vid, unsigned epoch) {
+  cons_sync();
+  if (threadIdx.x == 0) st_release_u32(flags + vid, epoch);
+}
+template <typename Pred>
+__device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned epoch, int ncta, Pred need, const Watch& w, int code) {
+  if (static_cast<int>(threadIdx.x) < ncta && need(static_cast<int>(threadIdx.x))) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(flags + threadIdx.x) != epoch) ds_repoll(w, spins, code);
+  }
+  cons_sync();
+}
+// elements [k0, k0+KP) of each of the B rows of a dense fp16 buffer: up to NLD 16-byte loads per thread, issued together
+template <int NLD>
+__device__ __forceinline__ void dense_issue(uint4 (&v)[NLD], const __half* src, int ld, int B, int k0, int KP) {
+  const int per_row = KP >> 3;
+  const int total = B * per_row;
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int idx = i * GV_CONS + threadIdx.x;
+    if (idx < total) {
+      const int b = idx / per_row, j = idx - b * per_row;
+      v[i] = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(b) * ld + k0) + j);
+    }
+  }
+}
+template <int NLD>
+__device__ __forceinline__ void dense_store(const uint4 (&v)[NLD], __half* xs, int pitch, int B, int KP) {
+  const int per_row = KP >> 3;
+  const int total = B * per_row;
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int idx = i * GV_CONS + threadIdx.x;
+    if (idx < total) {
+      const int b = idx / per_row, j = idx - b * per_row;
+      *reinterpret_cast<uint4*>(xs + static_cast<size_t>(b) * pitch + 8 * j) = v[i];
     }
   }
 }
@@ -227,7 +323,7 @@ __device__ __forceinline__ void stage_rms(__half* xs, int pitch, const uint2* sr
         const int b = c / cpr, j = (c - b * cpr) * GV_CONS + threadIdx.x;
         unsigned spins = 0;
         while (v[i].y != epoch || v[i].w != epoch) {
-          ds_watch(w, spins, 22);
+          ds_repoll(w, spins, 22);
           v[i] = ll_ld16(s4 + static_cast<size_t>(b) * (H >> 2) + j);
         }
         *reinterpret_cast<uint2*>(xs + static_cast<size_t>(b) * pitch + 4 * j) = make_uint2(v[i].x, v[i].z);
@@ -331,8 +427,8 @@ __device__ __forceinline__ float ds_part_out(const float* s_part, int idx) {
 }
 // tiles [t0,t1) of this CTA for one k-phase; tiles outside [tlo,thi) have no needed row (head phase) and are zeroed
 template <int NBC>
-__device__ __forceinline__ void consume_tiles(const DsSmem& m, int KP, int KS, int t0, int t1, int tlo, int thi, bool add, int B, int stages,
-                                              int& rs, uint32_t& rph, const Watch& w) {
+__device__ __forceinline__ void consume_tiles(const DsSmem& m, const __half* xs, int KP, int KS, int t0, int t1, int tlo, int thi, bool add, int B,
+                                              int stages, int& rs, uint32_t& rph, const Watch& w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ksw = KS / GV_WARPS;
@@ -341,7 +437,7 @@ __device__ __forceinline__ void consume_tiles(const DsSmem& m, int KP, int KS, i
   const int nks = KP / KS;
   const bool xok = g < B;
   const bool full = nch == 4;
-  const __half* xbase = m.xs + g * (KP + XS_PAD) + warp * ksw + t * 8;
+  const __half* xbase = xs + g * (KP + XS_PAD) + warp * ksw + t * 8;
   for (int tile = t0; tile < t1; ++tile) {
     float* pt = m.s_part + (static_cast<size_t>(tile - t0) * GV_WARPS + warp) * (GV_TILE * NBC);
     float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -369,9 +465,9 @@ __device__ __forceinline__ void consume_tiles(const DsSmem& m, int KP, int KS, i
 
 // epilogue of tiles [t0,t1): kind 0 store, 1 residual add (residual rows live in shared memory), 2 SwiGLU pairs.
 // Outputs leave as exchange units {2 adjacent outputs of one batch row, epoch}.
-template <int NBC>
-__device__ __forceinline__ void epilogue_ll(const DsSmem& m, int r0, int r1, int t0, int t1, int B, int kind, uint2* out_ll, int row_units,
-                                            unsigned epoch, __half* s_res) {
+template <int NBC, bool DENSE>
+__device__ __forceinline__ void epilogue_ll(const DsSmem& m, int r0, int r1, int t0, int t1, int B, int kind, uint2* out_ll, __half* out_d,
+                                            int row_units, unsigned epoch, __half* s_res) {
   const int nout = (t1 - t0) * (GV_TILE * NBC);
   for (int base = 0; base < nout; base += GV_CONS) {            // warp-uniform trip count: the shuffles below are full-warp
     const int idx = base + threadIdx.x;
@@ -383,7 +479,10 @@ __device__ __forceinline__ void epilogue_ll(const DsSmem& m, int r0, int r1, int
       const float up = __shfl_xor_sync(0xffffffffu, v, NBC);                 // the next row of the same batch column
       const uint32_t a = half_bits(silu_f(v) * up);                          // meaningful on even rows
       const uint32_t a2 = __shfl_xor_sync(0xffffffffu, a, 2 * NBC);          // the next SwiGLU output
-      if (ok && (row & 3) == 0) ll_st8(out_ll + static_cast<size_t>(n) * row_units + (row >> 2), a | (a2 << 16), epoch);
+      if (ok && (row & 3) == 0) {
+        if (DENSE) __stcg(reinterpret_cast<unsigned*>(out_d + static_cast<size_t>(n) * (2 * row_units) + (row >> 1)), a | (a2 << 16));
+        else ll_st8(out_ll + static_cast<size_t>(n) * row_units + (row >> 2), a | (a2 << 16), epoch);
+      }
     } else {
       float r = v;
       if (kind == 1 && ok) r += __half2float(s_res[n * DS_RES_PITCH + (row - r0)]);
@@ -391,7 +490,10 @@ __device__ __forceinline__ void epilogue_ll(const DsSmem& m, int r0, int r1, int
       if (kind == 1 && ok) s_res[n * DS_RES_PITCH + (row - r0)] = h;
       const uint32_t hb = static_cast<uint32_t>(__half_as_ushort(h));
       const uint32_t hp = __shfl_xor_sync(0xffffffffu, hb, NBC);
-      if (ok && (row & 1) == 0) ll_st8(out_ll + static_cast<size_t>(n) * row_units + (row >> 1), hb | (hp << 16), epoch);
+      if (ok && (row & 1) == 0) {
+        if (DENSE) __stcg(reinterpret_cast<unsigned*>(out_d + static_cast<size_t>(n) * (2 * row_units) + row), hb | (hp << 16));
+        else ll_st8(out_ll + static_cast<size_t>(n) * row_units + (row >> 1), hb | (hp << 16), epoch);
+      }
     }
   }
 }
@@ -404,9 +506,9 @@ struct AttnCtl {
   int pages[64];
   float cs[DS_HD / 2], sn[DS_HD / 2];
 };
-__device__ __forceinline__ void attn_ctl_init(const DsParams& p, AttnCtl* c) {
+__device__ __forceinline__ void attn_ctl_init(const DsParams& p, AttnCtl* c, int vid) {
   const int items = p.B * p.kvh * p.nsplit;
-  const int it = blockIdx.x;
+  const int it = vid;
   if (threadIdx.x == 0) {
     c->valid = (it < items && p.layers > 0) ? 1 : 0;
     c->np = 0;
@@ -438,6 +540,7 @@ __device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1
 }
 
 // Work item (b, kv, split) on the 8 consumer warps.  Scratch lives in the s_part region.
+template <bool DENSE>
 __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, const AttnCtl& ctl, const DsSmem& m, float* scratch, int dl,
                                           unsigned ep_qkv, unsigned ep_part, unsigned ep_attn, int stages, int& rs, uint32_t& rph,
                                           const Watch& w) {
@@ -452,7 +555,23 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
   const float sl2 = rsqrtf(static_cast<float>(DS_HD)) * 1.4426950408889634f;    // softmax scale in the exp2 domain
 
   // ---- q (4 heads), and for split 0 the new k / v row, from the QKV exchange buffer: only this kv head's producers are awaited
-  {
+  if (DENSE) {
+    const int q0 = kv * DS_G * DS_HD, k0r = p.heads * DS_HD + kv * DS_HD, v0r = (p.heads + p.kvh) * DS_HD + kv * DS_HD;
+    const int grid = gridDim.x, qkvw = p.qkvw;
+    wait_flags(p.fq, ep_qkv, grid, [&](int c) {
+      int a0, a1;
+      rows_of_cta(p.cum, qkvw, 2, c, grid, a0, a1);
+      bool need = a0 < q0 + DS_G * DS_HD && a1 > q0;
+      if (split == 0) need = need || (a0 < k0r + DS_HD && a1 > k0r) || (a0 < v0r + DS_HD && a1 > v0r);
+      return need;
+    }, w, 41);
+    const __half* row = p.qkvd + static_cast<size_t>(b) * qkvw;
+    int src = -1, dst = 0;
+    if (tid < 64) { src = q0 + tid * 8; dst = tid * 8; }
+    else if (split == 0 && tid < 80) { src = k0r + (tid - 64) * 8; dst = 512 + (tid - 64) * 8; }
+    else if (split == 0 && tid < 96) { src = v0r + (tid - 80) * 8; dst = 640 + (tid - 80) * 8; }
+    if (src >= 0) *reinterpret_cast<uint4*>(raw + dst) = __ldcg(reinterpret_cast<const uint4*>(row + src));
+  } else {
     const uint4* row4 = reinterpret_cast<const uint4*>(p.qkv_ll + static_cast<size_t>(b) * (p.qkvw >> 1));
     int src = -1, dst = 0;
     if (tid < 128) { src = (kv * DS_G * DS_HD) / 4 + tid; dst = tid * 4; }
@@ -500,9 +619,13 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
     aq2[ks] = (g < DS_G) ? *reinterpret_cast<const uint32_t*>(qs + g * DS_HD + ks * 16 + 8 + 2 * t) : 0u;
   }
   float mrow = -INFINITY, lrow = 0.f;      // online softmax state of head g (exp2 domain), replicated over the quad
-  float o[16][4];
+  // O^T accumulators (dims in the M slot, the 4 heads in the N slot of m16n8k8): o[mt][0..1] = (dim 16mt+g, heads 2t, 2t+1),
+  // o[mt][2..3] = (dim 16mt+8+g, heads 2t, 2t+1); lanes with t >= 2 hold the padding heads 4..7.  Half the registers of
+  // O with the heads in the M slot (4 of 16 rows used).
+  float o[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  for (int mt = 0; mt < 8; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+  const int src_a = 8 * t, src_b = 8 * t + 4;                // lanes holding the softmax state of heads 2t and 2t+1
   for (int i = 0; i < ctl.np; ++i) {
     ds_mbar_wait(&m.full[rs], rph, w, 42);
     const __half* Kt = m.ws + static_cast<size_t>(rs) * DS_STAGE_HALVES;
@@ -531,19 +654,18 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
     ps += __shfl_xor_sync(0xffffffffu, ps, 2);
     lrow = lrow * corr + ps;
     mrow = mn;
-    const uint32_t ap = pack_half2(p0, p1);                  // A operand of m16n8k8: P[head g][keys 2t, 2t+1]
-    // O += P V : V fragments of the warp's 8 keys, 32 dims per ldmatrix.x4.trans
+    const uint32_t bp = (g < DS_G) ? pack_half2(p0, p1) : 0u;   // B operand of m16n8k8: P^T[keys 2t, 2t+1][head g]
+    const float ca = __shfl_sync(0xffffffffu, corr, src_a), cb = __shfl_sync(0xffffffffu, corr, src_b);
+    // O^T += V^T P^T : V^T fragments of the warp's 8 keys, 32 dims per ldmatrix.x4.trans
     const uint32_t vaddr = smem_u32(Vt + (8 * warp + (lane & 7)) * DS_HD);
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
       uint32_t v0, v1, v2, v3;
       ldmatrix_x4_trans(v0, v1, v2, v3, vaddr + ((((4 * q4 + (lane >> 3)) ^ (lane & 7)) << 3) << 1));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { o[4 * q4 + j][0] *= corr; o[4 * q4 + j][1] *= corr; }
-      mma_1688(o[4 * q4 + 0], ap, 0u, v0);
-      mma_1688(o[4 * q4 + 1], ap, 0u, v1);
-      mma_1688(o[4 * q4 + 2], ap, 0u, v2);
-      mma_1688(o[4 * q4 + 3], ap, 0u, v3);
+      o[2 * q4][0] *= ca; o[2 * q4][1] *= cb; o[2 * q4][2] *= ca; o[2 * q4][3] *= cb;
+      o[2 * q4 + 1][0] *= ca; o[2 * q4 + 1][1] *= cb; o[2 * q4 + 1][2] *= ca; o[2 * q4 + 1][3] *= cb;
+      mma_1688(o[2 * q4], v0, v1, bp);
+      mma_1688(o[2 * q4 + 1], v2, v3, bp);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&m.empty[rs]);
@@ -563,20 +685,30 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
     const float pr = exp2f(s - mn), corr = exp2f(mrow - mn);
     lrow = lrow * corr + pr;
     mrow = mn;
+    const float ca = __shfl_sync(0xffffffffu, corr, src_a), cb = __shfl_sync(0xffffffffu, corr, src_b);
+    const float pa = __shfl_sync(0xffffffffu, pr, src_a), pb = __shfl_sync(0xffffffffu, pr, src_b);
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      o[nt][0] = o[nt][0] * corr + pr * vnew[nt * 8 + 2 * t];
-      o[nt][1] = o[nt][1] * corr + pr * vnew[nt * 8 + 2 * t + 1];
+    for (int mt = 0; mt < 8; ++mt) {
+      const float va = vnew[16 * mt + g], vb = vnew[16 * mt + 8 + g];
+      o[mt][0] = o[mt][0] * ca + pa * va;
+      o[mt][1] = o[mt][1] * cb + pb * va;
+      o[mt][2] = o[mt][2] * ca + pa * vb;
+      o[mt][3] = o[mt][3] * cb + pb * vb;
     }
   }
   stamp(p, dl, 21);
   // ---- CTA-level merge of the 8 warps' states ----
-  if (g < DS_G) {
+  if (t < 2) {
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt)
-      *reinterpret_cast<float2*>(red_o + (warp * DS_G + g) * DS_HD + nt * 8 + 2 * t) = make_float2(o[nt][0], o[nt][1]);
-    if (t == 0) { red_ml[(warp * DS_G + g) * 2] = mrow; red_ml[(warp * DS_G + g) * 2 + 1] = lrow; }
+    for (int mt = 0; mt < 8; ++mt) {
+      float* ra = red_o + (warp * DS_G + 2 * t) * DS_HD + 16 * mt + g;
+      ra[0] = o[mt][0];
+      ra[DS_HD] = o[mt][1];
+      ra[8] = o[mt][2];
+      ra[DS_HD + 8] = o[mt][3];
+    }
   }
+  if (g < DS_G && t == 0) { red_ml[(warp * DS_G + g) * 2] = mrow; red_ml[(warp * DS_G + g) * 2 + 1] = lrow; }
   cons_sync();
   const int item = (b * p.kvh + kv) * p.nsplit + split;
   {
@@ -618,8 +750,8 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
         for (int k = 0; k < 4; ++k) {
           if (s0 + k < p.nsplit) {
             unsigned spins = 0;
-            while (ml[k].y != ep_part || ml[k].w != ep_part) { ds_watch(w, spins, 43); ml[k] = ll_ld16(p.part_ml_ll + (gi + s0 + k) * DS_G + h); }
-            while (po[k].y != ep_part || po[k].w != ep_part) { ds_watch(w, spins, 44); po[k] = ll_ld16(p.part_o_ll + (gi + s0 + k) * (DS_G * DS_HD) + D); }
+            while (ml[k].y != ep_part || ml[k].w != ep_part) { ds_repoll(w, spins, 43); ml[k] = ll_ld16(p.part_ml_ll + (gi + s0 + k) * DS_G + h); }
+            while (po[k].y != ep_part || po[k].w != ep_part) { ds_repoll(w, spins, 44); po[k] = ll_ld16(p.part_o_ll + (gi + s0 + k) * (DS_G * DS_HD) + D); }
             const float ms = __uint_as_float(ml[k].x), ls = __uint_as_float(ml[k].z);
             if (ls != 0.f) {
               const float mn = fmaxf(M, ms);
@@ -633,7 +765,8 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
         }
       }
       const float inv = 1.f / Ls;
-      ll_st8(p.attn_ll + static_cast<size_t>(b) * (p.qd >> 1) + ((kv * DS_G * DS_HD + D) >> 1), pack_half2(a0 * inv, a1 * inv), ep_attn);
+      if (DENSE) __stcg(reinterpret_cast<unsigned*>(p.attnd + static_cast<size_t>(b) * p.qd + kv * DS_G * DS_HD + D), pack_half2(a0 * inv, a1 * inv));
+      else ll_st8(p.attn_ll + static_cast<size_t>(b) * (p.qd >> 1) + ((kv * DS_G * DS_HD + D) >> 1), pack_half2(a0 * inv, a1 * inv), ep_attn);
     }
   }
   stamp(p, dl, 23);
@@ -817,7 +950,7 @@ __device__ __forceinline__ PhaseGeo phase_geo(const DsParams& p, int type) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __grid_constant__ DsParams p) {
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __grid_constant__ DsParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   DsSmem m;
   {
@@ -838,7 +971,9 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
   Watch w;
   w.t0 = gtimer();
   w.err = p.err;
-  for (int i = threadIdx.x; i < p.layers * static_cast<int>(sizeof(DsLayer) / 8); i += GV_THREADS)
+  w.sleep_ns = static_cast<unsigned>(p.poll_sleep_ns);
+  w.limit_ns = static_cast<unsigned long long>(p.watchdog_ms) * 1000000ull;
+  for (int i = threadIdx.x; i < p.layers * static_cast<int>(sizeof(DsLayer) / 8); i += DS_THREADS)
     reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.L)[i];
   // active-head row ranges: read ONCE, before CTA 0's finalize of this step can rewrite heads[]
   if (threadIdx.x < GV_MAXB) {
@@ -855,7 +990,14 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
     }
     fence_barrier_init();
   }
-  attn_ctl_init(p, &s_ctl);                                     // contains __syncthreads
+  int vid = blockIdx.x;
+  if (p.cum != nullptr) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= gridDim.x) ds_die(p.err, 61);                   // SM ids are not 0..gridDim-1 here: run with TRACE_B200_BALANCE=0
+    vid = static_cast<int>(smid);
+  }
+  attn_ctl_init(p, &s_ctl, vid);                                // contains __syncthreads
   const int ncta = gridDim.x;
   int ulo = 0x7fffffff, uhi = 0;
   for (int b = 0; b < p.B; ++b) { ulo = min(ulo, s_hlo[b]); uhi = max(uhi, s_hhi[b]); }
@@ -863,6 +1005,8 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
   const int do_sample = p.st.ctrl[3];
 
   if (threadIdx.x >= GV_CONS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DS_REGS_PRODUCER));
+    if (threadIdx.x >= GV_CONS + 32) return;
     // ===================== producer warp: everything the step reads from HBM, in program order =====================
     int s = 0;
     uint32_t ph = 0;
@@ -871,7 +1015,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
       const DsLayer& L = s_layers[type == 4 ? 0 : l];
       const PhaseGeo g = phase_geo(p, type);
       int r0, r1;
-      ds_rows(g.N, g.unit, r0, r1);
+      rows_of_cta(p.cum, g.N, g.unit, vid, ncta, r0, r1);
       const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
       const __half* W = type == 0 ? L.qkv_w : type == 1 ? L.o_w : type == 2 ? L.gateup_w : type == 3 ? L.down_w : p.head_w;
       if (vlo < vhi) produce_matrix(W, g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, w);
@@ -894,18 +1038,22 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
   }
 
   // ===================== consumer warps =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DS_REGS_CONSUMER));
   int rs = 0;
   uint32_t rph = 0;
   int xr0, xr1;
-  ds_rows(p.H, 2, xr0, xr1);
+  rows_of_cta(p.cum, p.H, 2, vid, ncta, xr0, xr1);
   // residual rows of this CTA (the O and down projections share one row partition): kept in shared memory for the whole step
   for (int i = threadIdx.x; i < p.B * DS_RES_PITCH; i += GV_CONS) {
     const int n = i / DS_RES_PITCH, r = i % DS_RES_PITCH;
     if (xr0 + r < xr1) s_res[i] = p.x[static_cast<size_t>(n) * p.H + xr0 + r];
   }
   cons_sync();
-  constexpr int NLD = NB <= 2 ? 8 : 16;
+  constexpr int NLD = NB <= 2 ? 8 : 16;     // (16 polls in flight per thread make ptxas spill the batch-1 kernel: a spill is an L2 round trip here)
+  constexpr bool DENSE = NB >= 4;
   const int xpitch_h = p.H + XS_PAD;
+  unsigned long long t_phase = 0, t_stream = 0;      // thread 0: time from "input staged" to "last stage consumed", summed over the phases
+  const auto all_ctas = [](int) { return true; };
 
   for (int seq = 0; seq < nseq; ++seq) {
     const int type = seq == nseq - 1 ? 4 : (seq & 3), l = type == 4 ? max(p.layers - 1, 0) : (seq >> 2);
@@ -913,7 +1061,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
     const PhaseGeo g = phase_geo(p, type);
     const unsigned epl = ep0 + 8u * static_cast<unsigned>(l);
     int r0, r1;
-    ds_rows(g.N, g.unit, r0, r1);
+    rows_of_cta(p.cum, g.N, g.unit, vid, ncta, r0, r1);
     const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
     const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
     int tlo = 0, thi = 0;
@@ -924,33 +1072,69 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
     const int ncol = threadIdx.x % NB;
     if (vlo < vhi) {
       // ---- input vector of the phase ----
-      if (pro) {
+      // x comes from: the dense input embedding (first phase of the launch), the O phase (gate/up), the previous layer's
+      // down phase (QKV, head)
+      const unsigned epx = type == 2 ? epl + 4 : (ep0 + 8u * static_cast<unsigned>(type == 4 ? p.layers - 1 : l - 1) + 6);
+      if (pro && DENSE) {      // (both branches compile for every NB; the dead one is eliminated)
+        const GammaRegs gm = load_gamma(type == 0 ? L.ln1 : type == 2 ? L.ln2 : p.final_norm, p.H);
+        if (seq > 0) wait_flags(p.fx, epx, ncta, all_ctas, w, 22);
+        stage_x_rmsnorm_nb<NB>(m.xs, seq == 0 ? p.x : p.xd, p.H, p.B, p.H, gm, p.eps, m.s_red);
+      } else if (pro) {
         const Gamma4 gm = load_gamma4(type == 0 ? L.ln1 : type == 2 ? L.ln2 : p.final_norm, p.H);
-        // x comes from: the dense input embedding (first phase of the launch), the O phase (gate/up), the previous layer's
-        // down phase (QKV, head)
         const bool dense = seq == 0;
-        const unsigned epx = type == 2 ? epl + 4 : (ep0 + 8u * static_cast<unsigned>(type == 4 ? p.layers - 1 : l - 1) + 6);
         stage_rms<NLD>(m.xs, xpitch_h, dense ? nullptr : p.x_ll, p.x, p.B, p.H, gm, p.eps, m.s_red, dense ? 0u : epx, w);
       }
       const int nkp = g.K / g.KP;
-      for (int k0 = 0; k0 < g.K; k0 += g.KP) {
-        if (!pro) {
+      const int xs_buf = p.B * (g.KP + XS_PAD);          // halves per staging buffer of a k-phase
+      // dense mode: the next k-phase's activations are in flight (registers) while this one is consumed.  Batch 8: k-phases of
+      // 2048 columns, two staging buffers.  Batch 4: k-phases of 7168 columns (14 loads per thread), one buffer.
+      constexpr bool DBUF = NB >= 8;
+      constexpr int PF = DBUF ? NB : 14;
+      uint4 pre[PF];
+      if constexpr (DENSE) if (!pro) {
+        wait_flags(type == 1 ? p.fa : p.fact, type == 1 ? epl + 3 : epl + 5, ncta, all_ctas, w, 21);
+        const __half* src = type == 1 ? p.attnd : p.actd;
+        if (nkp == 1) {                                   // whole input in one batch (KP <= 4096: 2*NB loads per thread)
+          uint4 v[2 * NB];
+          dense_issue<2 * NB>(v, src, g.K, p.B, 0, g.KP);
+          dense_store<2 * NB>(v, m.xs, g.KP + XS_PAD, p.B, g.KP);
+        } else {                                          // k-phased
+          dense_issue<PF>(pre, src, g.K, p.B, 0, g.KP);
+          dense_store<PF>(pre, m.xs, g.KP + XS_PAD, p.B, g.KP);
+        }
+      }
+      for (int k0 = 0, kpi = 0; k0 < g.K; k0 += g.KP, ++kpi) {
+        const __half* xcur = m.xs;
+        if (!pro && !DENSE) {
           if (k0 > 0) cons_sync();
           if (type == 1) stage_ll<NLD>(m.xs, g.KP + XS_PAD, p.attn_ll, p.qd >> 1, p.B, k0, g.KP, epl + 3, w);
           else stage_ll<NLD>(m.xs, g.KP + XS_PAD, p.act_ll, p.ffn >> 1, p.B, k0, g.KP, epl + 5, w);
         }
-        cons_sync();
+        cons_sync();                                      // staged activations visible; every warp is done with the previous k-phase
+        if constexpr (DENSE) if (!pro) {
+          if (DBUF) xcur = m.xs + (kpi & 1) * xs_buf;
+          if (k0 + g.KP < g.K) dense_issue<PF>(pre, type == 1 ? p.attnd : p.actd, g.K, p.B, k0 + g.KP, g.KP);
+        }
         if (k0 == 0) stamp(p, l, 10 + type * 2);
+        if (k0 == 0 && type < 4 && threadIdx.x == 0) t_phase = gtimer();
         const int gt = nkp > 1 ? ntile : p.group_tiles;
         for (int t0 = 0; t0 < ntile; t0 += gt) {
           const int t1 = min(ntile, t0 + gt);
-          consume_tiles<NB>(m, g.KP, g.KS, t0, t1, tlo, thi, k0 > 0, p.B, p.stages, rs, rph, w);
-          if (k0 + g.KP < g.K) continue;         // more k-phases to accumulate
+          consume_tiles<NB>(m, xcur, g.KP, g.KS, t0, t1, tlo, thi, k0 > 0, p.B, p.stages, rs, rph, w);
+          if (k0 + g.KP < g.K) {                 // more k-phases to accumulate
+            if constexpr (DENSE) if (!pro) {
+              if (!DBUF) cons_sync();            // one buffer: every warp is done reading it
+              dense_store<PF>(pre, m.xs + (DBUF ? ((kpi + 1) & 1) * xs_buf : 0), g.KP + XS_PAD, p.B, g.KP);
+            }
+            continue;
+          }
           cons_sync();
-          if (type == 0) epilogue_ll<NB>(m, r0, r1, t0, t1, p.B, 0, p.qkv_ll, p.qkvw >> 1, epl + 1, s_res);
-          else if (type == 1) epilogue_ll<NB>(m, r0, r1, t0, t1, p.B, 1, p.x_ll, p.H >> 1, epl + 4, s_res);
-          else if (type == 2) epilogue_ll<NB>(m, r0, r1, t0, t1, p.B, 2, p.act_ll, p.ffn >> 1, epl + 5, s_res);
-          else if (type == 3) epilogue_ll<NB>(m, r0, r1, t0, t1, p.B, 1, p.x_ll, p.H >> 1, epl + 6, s_res);
+          if (t1 == ntile) stamp(p, l, 24 + type);
+          if (t1 == ntile && type < 4 && threadIdx.x == 0) t_stream += gtimer() - t_phase;
+          if (type == 0) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 0, p.qkv_ll, p.qkvd, p.qkvw >> 1, epl + 1, s_res);
+          else if (type == 1) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 1, p.x_ll, p.xd, p.H >> 1, epl + 4, s_res);
+          else if (type == 2) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 2, p.act_ll, p.actd, p.ffn >> 1, epl + 5, s_res);
+          else if (type == 3) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 1, p.x_ll, p.xd, p.H >> 1, epl + 6, s_res);
           else {
             // ---- heads: logits of the active ranges (fp16-rounded like the reference's fp16 GEMM) + argmax candidates ----
             const int lo = s_hlo[ncol], hi = s_hhi[ncol];
@@ -977,10 +1161,13 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
         if (ncol < p.B && r < r1 && r < p.n_valid) p.logits_out[static_cast<size_t>(ncol) * p.n_valid + r] = -INFINITY;
       }
     }
+    if (DENSE && type < 4)                        // every CTA publishes every exchange, rows or not
+      publish(type == 0 ? p.fq : type == 2 ? p.fact : p.fx, vid, type == 0 ? epl + 1 : type == 1 ? epl + 4 : type == 2 ? epl + 5 : epl + 6);
     if (type == 0) {
       cons_sync();                               // the partial-sum buffer becomes the attention scratch
-      if (s_ctl.valid) attn_item(p, L, s_ctl, m, m.s_part, l, epl + 1, epl + 2, epl + 3, p.stages, rs, rph, w);
+      if (s_ctl.valid) attn_item<DENSE>(p, L, s_ctl, m, m.s_part, l, epl + 1, epl + 2, epl + 3, p.stages, rs, rph, w);
       stamp(p, l, 3);
+      if (DENSE) publish(p.fa, vid, epl + 3);
       cons_sync();
     } else if (type == 4) {
 #pragma unroll
@@ -1001,12 +1188,13 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stream_kernel(const __gr
           if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
         }
         if (do_sample) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // sampling reads the logits after the candidate line
-        ll_st16(p.cand_ll + static_cast<size_t>(threadIdx.x) * ncta + blockIdx.x, __float_as_uint(v), static_cast<uint32_t>(i),
+        ll_st16(p.cand_ll + static_cast<size_t>(threadIdx.x) * ncta + vid, __float_as_uint(v), static_cast<uint32_t>(i),
                 ep0 + 8u * static_cast<unsigned>(p.layers) + 1);
       }
     }
   }
-  if (blockIdx.x == 0) {
+  if (threadIdx.x == 0 && p.stream_ns != nullptr && p.layers > 0) p.stream_ns[vid] += static_cast<unsigned>(t_stream);   // the host reads and clears it
+  if (vid == 0) {
     cons_sync();
     finalize_step(p, ncta, ep0 + 8u * static_cast<unsigned>(p.layers) + 1, s_hlo, s_hhi, w);
   }
@@ -1029,8 +1217,9 @@ static int ds_pick_ks(int KP) {
   return 0;
 }
 
-size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sms, size_t* offs /*[8]*/) {
-  // x | qkv | attn | act | part_o | part_ml | cand | (end); 8-byte units, every region 256-byte aligned
+size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sms, size_t* offs /*[16]*/) {
+  // flag-in-data regions: x | qkv | attn | act | part_o | part_ml | cand; dense regions (batch >= 4): x | qkv | attn | act | 4 flag arrays;
+  // every region 256-byte aligned
   size_t o = 0;
   auto put = [&](int i, size_t bytes) { offs[i] = o; o += (bytes + 255) & ~static_cast<size_t>(255); };
   put(0, static_cast<size_t>(GV_MAXB) * (H / 2) * 8);
@@ -1040,7 +1229,12 @@ size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sm
   put(4, static_cast<size_t>(num_sms) * DS_G * DS_HD * 8);
   put(5, static_cast<size_t>(num_sms) * DS_G * 16);
   put(6, static_cast<size_t>(GV_MAXB) * num_sms * 16);
-  offs[7] = o;
+  put(7, static_cast<size_t>(GV_MAXB) * H * 2);
+  put(8, static_cast<size_t>(GV_MAXB) * qkvw * 2);
+  put(9, static_cast<size_t>(GV_MAXB) * qd * 2);
+  put(10, static_cast<size_t>(GV_MAXB) * ffn * 2);
+  put(11, static_cast<size_t>(4) * num_sms * 4);
+  offs[12] = o;
   return o;
 }
 
@@ -1055,15 +1249,25 @@ static int ds_plan(const DecodeStreamArgs& a, DsParams& p, size_t* smem_out) {
   TB_CHECK(a.ffn % 4 == 0 && a.qkvw % 4 == 0 && a.head_rows % 2 == 0, "row counts must divide into exchange units");
   TB_CHECK(a.num_sms <= GV_CONS, "candidate merge handles <= 256 CTAs");
   const size_t xcap = 72 * 1024;
+  const bool nbc8 = B > 4;
+  const bool dense = B > 2;            // batch bucket >= 4: dense exchange, k-phased down projection with double-buffered staging
   const int Ks[5] = {a.H, a.qd, a.H, a.ffn, a.H};
   int kpmax = 0;
   for (int i = 0; i < 5; ++i) {
-    const int kp = ds_pick_kp(Ks[i], B, xcap);
+    int kp = ds_pick_kp(Ks[i], B, xcap);
+    if (nbc8 && i == 3 && kp > 2048) {            // batch 8: double-buffered k-phases of <= 2048 columns
+      kp = 0;
+      for (int c = 2048; c >= 256 && kp == 0; c -= (c > 1024 ? 1024 : 256))
+        if (Ks[i] % c == 0) kp = c;
+    }
+    if (dense && !nbc8 && i == 3) TB_CHECK(kp <= 7168, "batch-4 down projection prefetches k-phases of <= 7168 columns");
+    if (dense && i == 1) TB_CHECK(kp == Ks[i] && kp <= 4096, "dense O-projection staging handles K <= 4096 in one batch");
     TB_CHECK(kp > 0, "decode GEMV K must be a multiple of 256");
     if (i == 0 || i == 2 || i == 4) TB_CHECK(kp == Ks[i], "fused RMSNorm needs the whole hidden row staged");
     p.kp[i] = kp;
     p.ks[i] = ds_pick_ks(kp);
-    if (kp > kpmax) kpmax = kp;
+    const int need = (nbc8 && i == 3 && kp < Ks[i]) ? 2 * (kp + XS_PAD) - XS_PAD : kp;     // batch 8: two staging buffers for the k-phased projection
+    if (need > kpmax) kpmax = need;
   }
   const int nbc = B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8;
   const int Ns[5] = {a.qkvw, a.H, 2 * a.ffn, a.H, a.head_rows};
@@ -1076,7 +1280,9 @@ static int ds_plan(const DecodeStreamArgs& a, DsParams& p, size_t* smem_out) {
     if (Ks[i] / p.kp[i] > 1) TB_CHECK(t * GV_WARPS * GV_TILE * nbc * 4 <= 28 * 1024, "k-phased projection with too many row tiles per CTA");
     if (i == 1 || i == 3) TB_CHECK(rows <= DS_RES_PITCH, "residual rows per CTA exceed the shared-memory residual buffer");
   }
-  int group_tiles = (28 * 1024) / (GV_WARPS * GV_TILE * nbc * 4);
+  // partial sums of a tile group: 28 KB, except at batch 8 where the region is sized by the attention scratch (20 KB) --
+  // that is what leaves room for a 4th ring stage next to the 66 KB of staged activations
+  int group_tiles = ((nbc == 8 ? 20 : 28) * 1024) / (GV_WARPS * GV_TILE * nbc * 4);
   if (group_tiles > max_tiles) group_tiles = max_tiles;
   int nsplit = a.num_sms / (B * a.kvh);
   if (nsplit < 1) nsplit = 1;
@@ -1118,11 +1324,11 @@ static int ds_launch(const DsParams& p, int grid, size_t smem, bool cooperative,
   }
   // every CTA must be resident at once (CTAs wait for each other's data): a cooperative launch makes the driver check it
   int per_sm = 0;
-  TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GV_THREADS, smem));
+  TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DS_THREADS, smem));
   TB_CHECK(per_sm >= 1, "fused decode step does not fit one CTA per SM");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GV_THREADS);
+  cfg.blockDim = dim3(DS_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1151,17 +1357,20 @@ int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream) {
   p.vocab = a.vocab; p.head_rows = a.head_rows; p.n_valid = a.n_valid; p.eps = a.eps;
   p.L = reinterpret_cast<const DsLayer*>(a.layer_table_dev);
   p.final_norm = a.final_norm; p.head_w = a.head_w; p.x = a.x; p.x_next = a.x;
-  size_t offs[8];
+  size_t offs[16];
   decode_stream_exchange_bytes(a.H, a.qkvw, a.qd, a.ffn, a.num_sms, offs);
   uint8_t* ex = static_cast<uint8_t*>(a.exchange);
   p.x_ll = reinterpret_cast<uint2*>(ex + offs[0]); p.qkv_ll = reinterpret_cast<uint2*>(ex + offs[1]);
   p.attn_ll = reinterpret_cast<uint2*>(ex + offs[2]); p.act_ll = reinterpret_cast<uint2*>(ex + offs[3]);
   p.part_o_ll = reinterpret_cast<uint2*>(ex + offs[4]); p.part_ml_ll = reinterpret_cast<uint4*>(ex + offs[5]);
   p.cand_ll = reinterpret_cast<uint4*>(ex + offs[6]);
+  p.xd = reinterpret_cast<__half*>(ex + offs[7]); p.qkvd = reinterpret_cast<__half*>(ex + offs[8]);
+  p.attnd = reinterpret_cast<__half*>(ex + offs[9]); p.actd = reinterpret_cast<__half*>(ex + offs[10]);
+  p.fx = reinterpret_cast<unsigned*>(ex + offs[11]); p.fq = p.fx + a.num_sms; p.fa = p.fq + a.num_sms; p.fact = p.fa + a.num_sms;
   p.cos_tab = a.cos_tab; p.sin_tab = a.sin_tab; p.block_table = a.block_table; p.max_pages = a.max_pages;
   p.logits_out = a.logits_out; p.samp_logits = a.samp_logits;
   p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
-  p.st = a.st; p.epoch_ctr = a.epoch_ctr; p.err = a.err; p.advance = a.advance; p.dbg = a.dbg;
+  p.st = a.st; p.epoch_ctr = a.epoch_ctr; p.err = a.err; p.advance = a.advance; p.dbg = a.dbg; p.poll_sleep_ns = a.poll_sleep_ns; p.cum = a.cum; p.stream_ns = a.stream_ns; p.watchdog_ms = a.watchdog_ms > 0 ? a.watchdog_ms : 4000;
   size_t smem = 0;
   if (ds_plan(a, p, &smem)) return 1;
   int rc;

@@ -9,11 +9,18 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, free when no tool is attached
+
 #include "../../include/trace_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 
 namespace tb {
+
+struct NvtxRange {            // one named range per stage of the path (tracing)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -98,6 +105,12 @@ struct trace_b200_ctx {
   int tm_relay = 0, gate_mode = 1, pf_ahead = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
   bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
   // fused decode step, v2 (decode_stream.cu)
+  int poll_sleep_ns = 0, watchdog_ms = 4000;
+  int balance = 1;                // TRACE_B200_BALANCE=0: equal rows per CTA instead of rows proportional to the SM's measured bandwidth share
+  float* d_cum = nullptr;
+  unsigned* d_stream_ns = nullptr;
+  std::vector<float> sm_share;    // current row share per SM id, relative to uniform
+  int balance_rounds = 0;         // feedback rounds applied so far (stops at kBalanceRounds)
   int decode_v = 2;               // TRACE_B200_DECODE=1 selects the round-1 kernel (decode_mega.cu) with its own KV layout
   int cooperative = 1;
   void* d_exchange = nullptr;
@@ -251,7 +264,7 @@ int allocate_all(trace_b200_ctx* ctx) {
       dalloc(ctx, &ctx->st.slot_ids, kMaxB, true))
     return 1;
   if (dalloc(ctx, &ctx->d_gbar, 4, true)) return 1;
-  if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 32, true)) return 1;
+  if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 32 + static_cast<size_t>(ctx->num_sms) * 32, true)) return 1;
   {
     const char* env = getenv("TRACE_B200_DECODE_PEROP");
     ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
@@ -274,6 +287,9 @@ int allocate_all(trace_b200_ctx* ctx) {
     ctx->decode_v = env_int("TRACE_B200_DECODE", 1, 2, 2);
     ctx->cooperative = env_int("TRACE_B200_COOP", 0, 1, 1);
     if (ctx->decode_v == 2) ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
+    ctx->poll_sleep_ns = env_int("TRACE_B200_POLL_SLEEP", 0, 5000, 0);
+    ctx->balance = env_int("TRACE_B200_BALANCE", 0, 1, 1);
+    ctx->watchdog_ms = env_int("TRACE_B200_WATCHDOG_MS", 1, 3600000, 4000);    // compute-sanitizer runs need minutes
   }
   // ---- KV pool ----
   const size_t page_elems = static_cast<size_t>(c.kv_heads) * kPage * c.head_dim;
@@ -289,7 +305,7 @@ int allocate_all(trace_b200_ctx* ctx) {
     }
   }
   if (ctx->decode_v == 2) {
-    size_t offs[8];
+    size_t offs[16];
     ctx->exchange_bytes = decode_stream_exchange_bytes(c.hidden, ctx->qkvw, c.heads * c.head_dim, c.ffn, ctx->num_sms, offs);
     uint8_t* ex = nullptr;
     if (dalloc(ctx, &ex, ctx->exchange_bytes, true)) return 1;
@@ -541,7 +557,7 @@ DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* 
   a.exchange = ctx->d_exchange; a.cos_tab = ctx->rope_cos; a.sin_tab = ctx->rope_sin; a.block_table = ctx->d_block_table;
   a.logits_out = logits_out; a.samp_logits = ctx->d_samp_logits; a.embed = ctx->embed; a.time_tab = ctx->time_tab;
   a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab; a.st = ctx->sst; a.epoch_ctr = ctx->d_epoch; a.err = ctx->d_err;
-  a.advance = layers_run > 0 ? 1 : 0; a.cooperative = ctx->cooperative; a.max_stages = ctx->max_stages; a.dbg = ctx->d_dbg;
+  a.advance = layers_run > 0 ? 1 : 0; a.cooperative = ctx->cooperative; a.max_stages = ctx->max_stages; a.poll_sleep_ns = ctx->poll_sleep_ns; a.watchdog_ms = ctx->watchdog_ms; a.cum = ctx->d_cum; a.stream_ns = ctx->d_stream_ns; a.dbg = ctx->d_dbg;
   return a;
 }
 
@@ -549,6 +565,47 @@ DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* 
 int decode_step_v2(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, cudaStream_t s) {
   const DecodeStreamArgs a = stream_args(ctx, B, layers_run, logits_out);
   RUN(decode_stream_step(a, s));
+  return 0;
+}
+
+// Bandwidth-balanced row partition, closed loop: the last launch reported how long every SM spent in its streaming phases;
+// SMs that took longer than average get proportionally fewer rows (damped, clamped to +-12 % of uniform).  A few rounds
+// during the first bursts of a context's life are enough: the imbalance is a fixed property of the SM's position.
+constexpr int kBalanceRounds = 8;
+int rebalance(trace_b200_ctx* ctx, cudaStream_t s) {
+  if (ctx->d_cum == nullptr || ctx->balance_rounds >= kBalanceRounds) return 0;
+  const int n = ctx->num_sms;
+  std::vector<unsigned> ns(n);
+  TB_CUDA(cudaMemcpyAsync(ns.data(), ctx->d_stream_ns, n * 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  double mean = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ns[i] == 0) return 0;                       // an SM id never seen (or a head-only launch): leave the partition alone
+    mean += ns[i];
+  }
+  mean /= n;
+  TB_CUDA(cudaMemsetAsync(ctx->d_stream_ns, 0, n * 4, s));    // the kernel accumulates over the launches of a burst
+  if (mean < 2e6) return 0;                         // too short to measure (parity-test models): keep equal rows
+  double wsum = 0;
+  std::vector<double> wgt(n);
+  for (int i = 0; i < n; ++i) {
+    double r = ctx->sm_share[i] * (1.0 + 0.7 * (mean / ns[i] - 1.0));
+    if (r > 1.12) r = 1.12;
+    if (r < 0.88) r = 0.88;
+    wgt[i] = r;
+    wsum += r;
+  }
+  std::vector<float> cum(n + 1);
+  double acc = 0;
+  for (int i = 0; i < n; ++i) {
+    cum[i] = static_cast<float>(acc / wsum);
+    ctx->sm_share[i] = static_cast<float>(wgt[i] * n / wsum);
+    acc += wgt[i];
+  }
+  cum[n] = 1.0f;
+  TB_CUDA(cudaMemcpyAsync(ctx->d_cum, cum.data(), cum.size() * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaStreamSynchronize(s));                // `cum` is a stack vector
+  ++ctx->balance_rounds;
   return 0;
 }
 
@@ -641,6 +698,7 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
       ctx->launches_since_reset += burst;
       if (poll_done()) return 1;
       if (done) break;
+      if (rebalance(ctx, s)) return 1;
     }
   }
   TB_CUDA(cudaEventRecord(ctx->ev_t1, s));
@@ -745,6 +803,14 @@ int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
     }
     TB_CUDA(cudaMemcpy(ctx->d_layer_table, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice));
   }
+  if (ctx->decode_v == 2 && ctx->balance && ctx->d_cum == nullptr) {
+    // rows per SM start uniform and are adapted from the kernel's own per-SM streaming times (rebalance below)
+    ctx->sm_share.assign(ctx->num_sms, 1.0f);
+    std::vector<float> cum(ctx->num_sms + 1);
+    for (int i = 0; i <= ctx->num_sms; ++i) cum[i] = static_cast<float>(i) / ctx->num_sms;
+    if (dalloc(ctx, &ctx->d_cum, cum.size()) || dalloc(ctx, &ctx->d_stream_ns, ctx->num_sms, true)) return 1;
+    TB_CUDA(cudaMemcpy(ctx->d_cum, cum.data(), cum.size() * 4, cudaMemcpyHostToDevice));
+  }
   TB_CUDA(cudaDeviceSynchronize());
   ctx->finalized = true;
   return 0;
@@ -753,6 +819,7 @@ int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
 int trace_b200_encode_frames(trace_b200_ctx* ctx, const void* pixels, int F, void* slots_out, void* feats_out, void* stream) {
   TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
   TB_CHECK(pixels != nullptr && slots_out != nullptr && F >= 0, "bad arguments");
+  NvtxRange nvtx("trace_b200.encode_frames");
   TB_CUDA(cudaSetDevice(ctx->device));
   const trace_b200_config& c = ctx->c;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -772,6 +839,7 @@ int trace_b200_build_prefill(trace_b200_ctx* ctx, const int64_t* ids_dev, int B,
   TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
   TB_CHECK(ids_dev && embeds_out && B > 0 && L > 0 && T >= 0, "bad arguments");
   TB_CHECK(T == 0 || (slots != nullptr && time_ids_dev != nullptr), "slots / time ids missing");
+  NvtxRange nvtx("trace_b200.build_prefill");
   TB_CUDA(cudaSetDevice(ctx->device));
   RUN(splice_prefill(ids_dev, B, L, T, static_cast<const __half*>(slots), time_ids_dev, ctx->embed, ctx->time_tab, ctx->sync_tab,
                      ctx->c.vocab, ctx->c.hidden, static_cast<__half*>(embeds_out), static_cast<cudaStream_t>(stream)));
@@ -819,6 +887,7 @@ int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, co
   TB_CHECK(slots_host && embeds && B >= 1 && B <= kMaxB && S >= 1, "bad arguments");
   const trace_b200_config& c = ctx->c;
   TB_CHECK(static_cast<int64_t>(B) * S <= c.max_prefill_tokens, "prefill exceeds max_prefill_tokens");
+  NvtxRange nvtx("trace_b200.prefill");
   TB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int b = 0; b < B; ++b) {
@@ -843,6 +912,7 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
   TB_CHECK(slots_host && heads_inout_host && ids_out_host && n_out && B >= 1 && B <= kMaxB && max_new >= 1, "bad arguments");
   const trace_b200_config& c = ctx->c;
+  NvtxRange nvtx("trace_b200.decode");
   TB_CUDA(cudaSetDevice(ctx->device));
   // everything below runs on the engine's stream, ordered after the caller's stream (prefill was enqueued there)
   TB_CUDA(cudaEventRecord(ctx->ev_in, static_cast<cudaStream_t>(stream)));
@@ -959,6 +1029,15 @@ int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int 
   return 0;
 }
 
+int trace_b200_sm_shares(trace_b200_ctx* ctx, float* out, int capacity) {
+  TB_CHECK(ctx != nullptr && out != nullptr, "null argument");
+  const int n = ctx->d_cum != nullptr ? static_cast<int>(ctx->sm_share.size()) : 0;
+  TB_CHECK(capacity >= n, "buffer too small");
+  for (int i = 0; i < n; ++i) out[i] = ctx->sm_share[i];
+  return 0;
+}
+int trace_b200_sm_share_count(trace_b200_ctx* ctx) { return (ctx != nullptr && ctx->d_cum != nullptr) ? static_cast<int>(ctx->sm_share.size()) : 0; }
+
 int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8) {
   TB_CHECK(ctx != nullptr && out8 != nullptr, "null argument");
   TB_CHECK(ctx->decode_v == 2, "decode plan introspection needs the streamed decode step (TRACE_B200_DECODE=2)");
@@ -976,8 +1055,8 @@ int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx) { return ctx ? ctx->weight_
 int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity) {
   TB_CHECK(ctx != nullptr && out_host != nullptr, "null argument");
   TB_CHECK(ctx->d_dbg != nullptr, "timeline not enabled (set TRACE_B200_MEGA_TIMING=1 before creating the context)");
-  const int n = 2 * ctx->c.layers * 32;
-  TB_CHECK(capacity >= n, "timeline buffer too small");
+  const int n = 2 * ctx->c.layers * 32 + (capacity >= 2 * ctx->c.layers * 32 + ctx->num_sms * 32 ? ctx->num_sms * 32 : 0);
+  TB_CHECK(capacity >= 2 * ctx->c.layers * 32, "timeline buffer too small");
   TB_CUDA(cudaMemcpy(out_host, ctx->d_dbg, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -14,6 +14,9 @@
 //              fp16 -> 16-byte global stores; overlaps with the next tile's main loop through the
 //              tmem_full / tmem_empty barrier pair.
 // Roofline: tensor pipe. 2*M*N*K flop per launch.
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -500,7 +503,37 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D K-major fp16 tensor [rows, cols] with leading dimension ld (elements); box {64, box_rows}, 128B swizzle.
+// Descriptors are cached by (pointer, shape): the engine's weights and workspaces are allocated once, so after the first
+// clip every GEMM launch finds both of its maps here instead of calling into the driver twice (~900 launches per clip).
+struct TmapKey {
+  const void* ptr;
+  int rows, cols, ld, box_rows;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (static_cast<size_t>(k.rows) << 32) ^ static_cast<size_t>(k.cols) ^ (static_cast<size_t>(k.ld) << 17) ^ (static_cast<size_t>(k.box_rows) << 50);
+    return h;
+  }
+};
+int make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows);
 int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *map = it->second;
+    return 0;
+  }
+  if (make_tmap_uncached(map, ptr, rows, cols, ld, box_rows)) return 1;
+  if (cache.size() > 8192) cache.clear();       // callers with ever-changing pointers (tests) must not grow it without bound
+  cache.emplace(key, *map);
+  return 0;
+}
+int make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   TB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   TB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");

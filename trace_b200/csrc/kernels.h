@@ -163,12 +163,14 @@ struct DecodeStreamArgs {
   unsigned* epoch_ctr;           // device launch counter (starts at 1); exchange epochs derive from it
   int* err;                      // device error word written by the kernel's watchdog before it traps
   int advance;                   // 0: head-only launch on the prefill's last hidden state (layers must be 0), 1: a decoder pass
-  int cooperative, max_stages;
+  int cooperative, max_stages, poll_sleep_ns, watchdog_ms;
+  const float* cum;              // [num_sms+1] cumulative row share per SM id, or null = equal rows per CTA (by blockIdx)
+  unsigned* stream_ns;           // [num_sms] out (by SM id): nanoseconds this launch spent in its streaming phases, or null
   unsigned long long* dbg;
 };
 int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream);
 int decode_stream_plan(const DecodeStreamArgs& a, int t, int32_t* out /*[8]: nsplit, ncomb, K/V pages per attention item at context t, kp_down, ks_down, ring stages, tiles per epilogue group, smem bytes*/);
-size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sms, size_t* offs /*[8]*/);
+size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sms, size_t* offs /*[16]*/);
 int decode_stream_layer_bytes();
 
 }  // namespace tb

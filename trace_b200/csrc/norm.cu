@@ -97,6 +97,80 @@ __global__ void __launch_bounds__(NT) norm_kernel(const __half* x, int ldx, cons
   norm_row<MODE>(v, nv, D, w, b, eps, out + static_cast<size_t>(row) * ldo, red);
 }
 
+// One WARP per row (D = NV * 256, the row stays packed in NV uint4 registers per lane): no block barriers, 8 rows per CTA.
+// The one-CTA-per-row kernel above is latency-bound (four __syncthreads per 2 KB row: 28 us for the 18 464 rows of a ViT
+// chunk whose 76 MB of traffic is an L2 hit); this one is bound by the L2 / HBM stream.
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256) norm_warp_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ w,
+                                                        const __half* __restrict__ b, float eps, __half* __restrict__ out, int ldo, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int D = NV * 256;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
+  uint4 u[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) u[i] = xr[lane + 32 * i];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(u[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += (MODE == 0) ? f[j] : f[j] * f[j];
+  }
+  s = warp_sum(s);
+  float mean = 0.f, rstd;
+  if (MODE == 0) {
+    mean = s / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; q += d * d; }
+    }
+    q = warp_sum(q);
+    rstd = rsqrtf(q / D + eps);
+  } else {
+    rstd = rsqrtf(s / D + eps);
+  }
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    float f[8], wf[8], o[8];
+    unpack8(u[i], f);
+    unpack8(reinterpret_cast<const uint4*>(w)[c], wf);
+    if (MODE == 0) {
+      float bf[8];
+      unpack8(reinterpret_cast<const uint4*>(b)[c], bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * wf[j] + bf[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wf[j] * __half2float(__float2half_rn(f[j] * rstd));
+    }
+    orow[c] = pack8(o);
+  }
+}
+
+template <int MODE>
+bool launch_norm_warp(const __half* x, int ldx, const __half* w, const __half* b, float eps, __half* out, int ldo, int rows, int D,
+                      cudaStream_t stream) {
+  const int grid = (rows + 7) / 8;
+  switch (D) {
+    case 256: norm_warp_kernel<MODE, 1><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 512: norm_warp_kernel<MODE, 2><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 768: norm_warp_kernel<MODE, 3><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 1024: norm_warp_kernel<MODE, 4><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 1280: norm_warp_kernel<MODE, 5><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 2048: norm_warp_kernel<MODE, 8><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 4096: norm_warp_kernel<MODE, 16><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    default: return false;
+  }
+}
+
 __global__ void __launch_bounds__(NT) vit_embed_ln_kernel(const __half* patch, const __half* cls, const __half* pos,
                                                           const __half* ln_w, const __half* ln_b, float eps,
                                                           __half* out, int P, int D) {
@@ -147,7 +221,8 @@ int layernorm_f16(const __half* x, int ldx, const __half* w, const __half* b, fl
   TB_CHECK(D % 8 == 0 && D <= NT * 8 * MAXV, "LayerNorm width must be a multiple of 8 and <= 4096");
   TB_CHECK(ldx % 8 == 0 && ldo % 8 == 0, "row pitch must be 16-byte aligned");
   if (rows == 0) return 0;
-  norm_kernel<0><<<rows, NT, 0, stream>>>(x, ldx, w, b, eps, out, ldo, D);
+  if (!launch_norm_warp<0>(x, ldx, w, b, eps, out, ldo, rows, D, stream))
+    norm_kernel<0><<<rows, NT, 0, stream>>>(x, ldx, w, b, eps, out, ldo, D);
   TB_LAUNCH_OK();
   return 0;
 }
@@ -157,7 +232,8 @@ int rmsnorm_f16(const __half* x, int ldx, const __half* w, float eps, __half* ou
   TB_CHECK(D % 8 == 0 && D <= NT * 8 * MAXV, "RMSNorm width must be a multiple of 8 and <= 4096");
   TB_CHECK(ldx % 8 == 0 && ldo % 8 == 0, "row pitch must be 16-byte aligned");
   if (rows == 0) return 0;
-  norm_kernel<1><<<rows, NT, 0, stream>>>(x, ldx, w, nullptr, eps, out, ldo, D);
+  if (!launch_norm_warp<1>(x, ldx, w, nullptr, eps, out, ldo, rows, D, stream))
+    norm_kernel<1><<<rows, NT, 0, stream>>>(x, ldx, w, nullptr, eps, out, ldo, D);
   TB_LAUNCH_OK();
   return 0;
 }

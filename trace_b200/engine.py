@@ -22,7 +22,7 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_sm_share_count", "trace_b200_sm_shares", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
     "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
 ]
 
@@ -70,6 +70,8 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_set_sampling.argtypes = [vp, i32, f32, i32, ctypes.c_uint64]
     lib.trace_b200_set_forced_ids.argtypes = [vp, ctypes.POINTER(i64), i32, i32]
     lib.trace_b200_decode_plan.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_int32)]
+    lib.trace_b200_sm_share_count.argtypes = [vp]
+    lib.trace_b200_sm_shares.argtypes = [vp, ctypes.POINTER(f32), i32]
     lib.trace_b200_launch_count.argtypes = [vp]
     lib.trace_b200_launch_count.restype = i64
     lib.trace_b200_last_decode_timing.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
@@ -237,6 +239,15 @@ class Engine:
         keys = ("nsplit", "ncomb", "kv_tiles_per_item", "kp_down", "ks_down", "stages", "group_tiles", "smem_bytes")
         return dict(zip(keys, list(out)))
 
+    def sm_shares(self) -> List[float]:
+        """Measured HBM bandwidth share per SM id relative to uniform ([] when the balanced row partition is off)."""
+        n = int(self.lib.trace_b200_sm_share_count(self._h))
+        if n == 0:
+            return []
+        buf = (ctypes.c_float * n)()
+        _check(self.lib.trace_b200_sm_shares(self._h, buf, n))
+        return list(buf)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.trace_b200_launch_count(self._h))
@@ -247,11 +258,18 @@ class Engine:
         _check(self.lib.trace_b200_last_decode_timing(self._h, ctypes.byref(ms), ctypes.byref(st)))
         return ms.value, st.value
 
-    def debug_timeline(self):
-        n = 2 * self.dims.layers * 32
+    def debug_timeline(self, per_cta: bool = False):
+        """[2 CTAs][layers][32] %globaltimer stamps of the last decode step; with per_cta also [SMs][32] stamps of every CTA
+        for the middle layer (slot 31 = %smid)."""
+        n0 = 2 * self.dims.layers * 32
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        n = n0 + (sms * 32 if per_cta else 0)
         buf = (ctypes.c_uint64 * n)()
         _check(self.lib.trace_b200_debug_timeline(self._h, buf, n))
-        return torch.tensor(list(buf), dtype=torch.int64).view(2, self.dims.layers, 32)
+        t = torch.tensor(list(buf), dtype=torch.int64)
+        if per_cta:
+            return t[:n0].view(2, self.dims.layers, 32), t[n0:].view(sms, 32)
+        return t.view(2, self.dims.layers, 32)
 
     @property
     def weight_bytes(self) -> int:

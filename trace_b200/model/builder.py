@@ -17,10 +17,26 @@ from .. import synth
 from .trace_mistral import TraceMistralConfig, TraceMistralForCausalLM
 
 
-def _dims_from_hf_config(cfg: dict) -> synth.TraceDims:
-    """Mistral keys from config.json; the CLIP tower's geometry is not stored there in the reference (it loads
-    `mm_vision_tower` by name, trace_arch.py:34-36) -- an optional `vision_config` block overrides the ViT-L/14-336 defaults."""
-    v = cfg.get("vision_config", {}) or {}
+def _vision_tower_dir(cfg: dict, model_path: str):
+    """The directory `mm_vision_tower` names when it is a local path (trace_arch.py:34-36 builds the tower from
+    `config.mm_vision_tower`; clip_encoder.py:23-29 loads CLIPVisionModel + CLIPImageProcessor from it)."""
+    vt = cfg.get("mm_vision_tower")
+    if not vt:
+        return None
+    for cand in (vt, os.path.join(model_path, vt), os.path.join(os.path.dirname(os.path.abspath(model_path)), os.path.basename(str(vt)))):
+        if os.path.isdir(cand):
+            return cand
+    return None
+
+
+def _dims_from_hf_config(cfg: dict, tower_dir=None) -> synth.TraceDims:
+    """Mistral keys from config.json.  The CLIP tower's geometry is not stored there in the reference (it loads
+    `mm_vision_tower` by name, trace_arch.py:34-36): it is read from the tower directory's own config.json when that is a local
+    directory, or from an optional `vision_config` block; otherwise the ViT-L/14-336 defaults apply."""
+    v = dict(cfg.get("vision_config", {}) or {})
+    if tower_dir is not None and os.path.exists(os.path.join(tower_dir, "config.json")):
+        tc = json.load(open(os.path.join(tower_dir, "config.json")))
+        v = {**tc.get("vision_config", tc), **v}
     extra = {k2: v[k1] for k1, k2 in (("hidden_size", "vit_width"), ("num_attention_heads", "vit_heads"), ("num_hidden_layers", "vit_layers"),
                                       ("intermediate_size", "vit_mlp"), ("image_size", "image_size"), ("patch_size", "patch_size")) if k1 in v}
     return synth.TraceDims(
@@ -48,19 +64,36 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         tokenizer = synth.StandInTokenizer(d.vocab)
     else:
         cfg = json.load(open(os.path.join(model_path, "config.json")))
-        d = _dims_from_hf_config(cfg)
+        tower_dir = _vision_tower_dir(cfg, model_path)
+        d = _dims_from_hf_config(cfg, tower_dir)
         model = TraceMistralForCausalLM(TraceMistralConfig(d, **{k: v for k, v in cfg.items() if k not in ("vision_config", "architectures")}), device=dev, **kwargs)
         shards = sorted(glob.glob(os.path.join(model_path, "*.safetensors"))) or sorted(glob.glob(os.path.join(model_path, "pytorch_model*.bin")))
         if not shards:
             raise FileNotFoundError(f"no weight shards under {model_path}")
-        for sh in shards:
+        def read(sh):
             if sh.endswith(".safetensors"):
                 from safetensors.torch import load_file
-                part = load_file(sh, device="cpu")
-            else:
-                part = torch.load(sh, map_location="cpu")
-            for name, t in part.items():
+                return load_file(sh, device="cpu")
+            return torch.load(sh, map_location="cpu")
+
+        seen_tower = False
+        for sh in shards:
+            for name, t in read(sh).items():
+                seen_tower = seen_tower or name.startswith("model.vision_tower.")
                 model.engine.load_weight(name, t.half())
+        if not seen_tower:
+            # released checkpoints keep the (frozen) CLIP tower out of the LLM shards: it is loaded from `mm_vision_tower`
+            # (trace_arch.py:34-36, clip_encoder.py:23-29) under the prefix the state dict would have had
+            if tower_dir is None:
+                raise FileNotFoundError(f"the checkpoint has no vision tower weights and config.mm_vision_tower={cfg.get('mm_vision_tower')!r} "
+                                        "is not a local directory (there is no network)")
+            tsh = sorted(glob.glob(os.path.join(tower_dir, "*.safetensors"))) or sorted(glob.glob(os.path.join(tower_dir, "pytorch_model*.bin")))
+            if not tsh:
+                raise FileNotFoundError(f"no weight shards under {tower_dir}")
+            for sh in tsh:
+                for name, t in read(sh).items():
+                    if name.startswith("vision_model."):            # text tower / projections of a full CLIPModel are not used
+                        model.engine.load_weight("model.vision_tower.vision_tower." + name, t.half())
         model.engine.load_state_dict([])
         if any(os.path.exists(os.path.join(model_path, f)) for f in ("tokenizer.model", "tokenizer.json", "tokenizer_config.json")):
             from transformers import AutoTokenizer

@@ -207,12 +207,13 @@ class TraceMistralForCausalLM:
     __call__ = forward
 
     # ---- encode_images_or_videos (trace_arch.py:218-266) ------------------------------------------
-    def _encode_slots(self, clips: List[torch.Tensor]) -> torch.Tensor:
-        B, T = len(clips), clips[0].shape[0]
-        frames = torch.cat([c.to(self.device, torch.float16) for c in clips], 0).contiguous()
+    def _encode_slots(self, clips: List[torch.Tensor], presliced_T: Optional[int] = None) -> torch.Tensor:
+        """`presliced_T`: the clips hold only this rank's frame range of T-frame clips (trace_b200.parallel.generate_sharded)."""
+        B, T = len(clips), clips[0].shape[0] if presliced_T is None else presliced_T
+        frames = torch.cat([c.to(self.device, torch.float16, non_blocking=True) for c in clips], 0).contiguous()
         if self.dist_group is not None:
             from ..parallel import encode_frames_sharded
-            slots = encode_frames_sharded(self.engine, frames, B, T, self.dist_group)
+            slots = encode_frames_sharded(self.engine, frames, B, T, self.dist_group, presliced=presliced_T is not None)
         else:
             slots = self.engine.encode_frames(frames)
         return slots.view(B, T, synth.NUM_SLOTS, self.dims.hidden)

@@ -25,11 +25,17 @@ def shard_bounds(T: int, world: int, rank: int):
     return rank * per, (rank + 1) * per
 
 
-def encode_frames_sharded(engine, frames: torch.Tensor, B: int, T: int, group) -> torch.Tensor:
-    """frames [B*T,3,H,W] (every rank holds all clips) -> slots [B*T, 8, hidden] on every rank."""
+def encode_frames_sharded(engine, frames: torch.Tensor, B: int, T: int, group, presliced: bool = False) -> torch.Tensor:
+    """frames [B*T,3,H,W] (every rank holds all clips) -> slots [B*T, 8, hidden] on every rank.
+    `presliced`: `frames` already is this rank's slice [B*(T/G),3,H,W] (frames [r*T/G, (r+1)*T/G) of every clip) -- a rank
+    only ever needs its own frames, so a caller that loads clips from the host should upload just those."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(T, world, rank)
-    fr = frames.view(B, T, *frames.shape[1:])[:, lo:hi].reshape(B * (hi - lo), *frames.shape[1:]).contiguous()
+    if presliced:
+        assert frames.shape[0] == B * (hi - lo), f"presliced frames: expected {B * (hi - lo)} frames, got {frames.shape[0]}"
+        fr = frames.contiguous()
+    else:
+        fr = frames.view(B, T, *frames.shape[1:])[:, lo:hi].reshape(B * (hi - lo), *frames.shape[1:]).contiguous()
     local = engine.encode_frames(fr)                                   # [B*(T/G), 8, H]
     local = local.view(B, hi - lo, local.shape[1], local.shape[2])
     gathered = torch.empty((world * B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -47,13 +53,15 @@ def clips_of_rank(n_clips: int, world: int, rank: int):
 
 @torch.no_grad()
 def generate_sharded(model, input_ids: torch.Tensor, clips, video_timestamps, heads, max_new_tokens: int, group=None,
-                     eos_token_id=None, pad_token_id=None):
+                     eos_token_id=None, pad_token_id=None, local_slices: bool = False):
     """Multi-GPU generate for a batch of B clips (same T, same prompt length):
       1. every rank encodes frames [r*T/G, (r+1)*T/G) of ALL clips, one all-gather of the projected slot tokens rebuilds
          [B,T,8,H] everywhere (`encode_frames_sharded`);
       2. rank r splices / prefills / decodes clips r, r+G, ... (<= 8 rows per decode loop) -- no collective in the loop;
       3. the new ids and the final heads are exchanged once (tiny object all-gather) so that every rank returns the full
          [B, n] tensor in clip order, padded with `pad_token_id` like a batched `generate`, and `heads` is updated in place.
+    `local_slices`: `clips[i]` holds only this rank's frames of clip i ([T/G,3,H,W], frames shard_bounds(T, G, rank));
+    T is then taken from `video_timestamps`.
     `model` needs `_encode_slots`, `_generate_from_slots`, `device`, `generation_config` (TraceMistralForCausalLM)."""
     from .model.encoders import frame_time_ids
     group = group if group is not None else dist.group.WORLD
@@ -64,7 +72,7 @@ def generate_sharded(model, input_ids: torch.Tensor, clips, video_timestamps, he
     prev = model.dist_group
     model.dist_group = group
     try:
-        slots = model._encode_slots(list(clips))                                  # [B,T,8,H] on every rank
+        slots = model._encode_slots(list(clips), presliced_T=len(video_timestamps[0]) if local_slices else None)   # [B,T,8,H] on every rank
     finally:
         model.dist_group = prev
     mine = clips_of_rank(B, world, rank)
