@@ -115,13 +115,6 @@ int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int 
  * code paths of the full-size configurations (several K/V tiles per item, k-phased down projection) are the ones they run. */
 int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8);
 
-/* Row share of every SM in the decode step, relative to uniform (1.0), indexed by SM id.  The shares start at 1 and are
- * adapted from the per-SM streaming times the kernel reports during the first decode bursts (the SMs do not get equal
- * shares of the HBM bandwidth under saturation).  trace_b200_sm_share_count returns 0 when the balanced partition is off
- * (TRACE_B200_BALANCE=0). */
-int trace_b200_sm_share_count(trace_b200_ctx* ctx);
-int trace_b200_sm_shares(trace_b200_ctx* ctx, float* out, int capacity);
-
 /* Introspection used by bench.py: kernels launched by this context since creation, and bytes of weights. */
 int64_t trace_b200_launch_count(trace_b200_ctx* ctx);
 int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);

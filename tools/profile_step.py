@@ -38,10 +38,6 @@ model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frame
 for name, shape, kind in synth.param_specs(d):
     model.engine.load_weight(name, synth.synth_tensor(name, shape, kind, 0, device="cuda"))
 model.engine.load_state_dict([])
-sh = model.engine.sm_shares()
-if sh:
-    srt = sorted(sh)
-    print(f"SM bandwidth shares (relative to uniform): min {srt[0]:.3f} p10 {srt[len(srt) // 10]:.3f} median {srt[len(srt) // 2]:.3f} p90 {srt[9 * len(srt) // 10]:.3f} max {srt[-1]:.3f}")
 ids = torch.tensor([bench_prompt_ids(a.frames)] * a.batch, dtype=torch.int64, device="cuda")
 clips, stamps = [], []
 for b in range(a.batch):
@@ -71,6 +67,8 @@ elif os.environ.get("TRACE_B200_MEGA_TIMING"):
                ("o.epi", x[:, 25], x[:, 13]), ("gu.wait_x", x[:, 13], x[:, 14]), ("gu.stream", x[:, 14], x[:, 26]),
                ("gu.epi", x[:, 26], x[:, 15]), ("dn.wait_act", x[:, 15], x[:, 16]), ("dn.stream", x[:, 16], x[:, 27]),
                ("dn.epi", x[:, 27], x[:, 17])]
+        per_layer = (x[:, 17] - prev_dn)
+        print(f"   cta{c} per-layer us: " + " ".join(f"{float(v):.0f}" for v in per_layer) + f" | o.wait_attn per layer: " + " ".join(f"{float(v):.0f}" for v in (x[:, 12] - x[:, 23])))
         tot = float((x[:, 17] - prev_dn).mean())
         print(f"cta{c}: layer={tot:.2f} us | " + " ".join(f"{n}={float((b - a_).mean()):.2f}" for n, a_, b in seg))
         stream = sum(float((b - a_).mean()) for n, a_, b in seg if n.endswith(".stream"))

@@ -76,8 +76,6 @@ struct DsParams {
   int kp[5], ks[5];
   int part_bytes, stages, xs_cap, group_tiles;
   int advance;
-  const float* cum;                     // [gridDim+1] cumulative row share per SM id (null: uniform partition by blockIdx)
-  unsigned* stream_ns;                  // [gridDim] out: time this CTA spent in the four streaming phases of the step, by SM id
   int watchdog_ms;                      // every wait in the kernel traps after this long (a protocol error must not hang the GPU)
   int poll_sleep_ns;                    // back-off between re-polls of an exchange unit that has not arrived (0 = none)
   unsigned long long* dbg;
@@ -153,23 +151,15 @@ __device__ __forceinline__ uint4 ll_wait16(const void* p, unsigned epoch, const 
 }
 __device__ __forceinline__ uint32_t half_bits(float v) { return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(v))); }
 
-// Rows are dealt to the CTAs in units of `unit` (2: output pairs share one exchange unit; 4: two SwiGLU pairs do).  A CTA is
-// identified by `vid`: blockIdx, or -- with the bandwidth-balanced partition -- the id of the SM it runs on.  Under HBM
-// saturation the SMs do not get equal shares of the bandwidth (+-5 %, a fixed property of each SM's position: measured,
-// profiles/r02_decode_timeline.md), so with equal row counts every phase ends with the whole grid waiting for the same few
-// SMs.  `cum` holds the cumulative share per SM id, rows are dealt proportionally, and the shares come from the kernel
-// itself: every launch reports the time each SM spent streaming (`stream_ns`), and the engine nudges the shares towards
-// equal times during the first decode bursts (engine.cu: rebalance).  The arithmetic of a row does not depend on which CTA
-// computes it, so results are bit-identical under any partition.
-__device__ __forceinline__ void rows_of_cta(const float* cum, int N, int unit, int c, int grid, int& r0, int& r1) {
+// Rows are dealt to the CTAs in units of `unit` (2: output pairs share one exchange unit; 4: two SwiGLU pairs do): every CTA
+// streams the same number of weight bytes (+- one unit) whatever N is -- no wave quantisation.
+// (Tried and dropped, profiles/r02_decode_timeline.md: rows proportional to a measured per-SM bandwidth share, open loop from a
+// calibration kernel and closed loop from the kernel's own per-SM streaming times.  The systematic part of the per-CTA skew
+// is +-2 %, the rest changes with the row ranges themselves; neither variant moved the step time.)
+__device__ __forceinline__ void rows_of_cta(int N, int unit, int c, int grid, int& r0, int& r1) {
   const long long U = N / unit;
-  if (cum != nullptr) {
-    r0 = static_cast<int>(__float2ll_rn(static_cast<float>(U) * cum[c])) * unit;
-    r1 = (c == grid - 1) ? N : static_cast<int>(__float2ll_rn(static_cast<float>(U) * cum[c + 1])) * unit;
-  } else {
-    r0 = static_cast<int>(U * c / grid) * unit;
-    r1 = (c == grid - 1) ? N : static_cast<int>(U * (c + 1) / grid) * unit;
-  }
+  r0 = static_cast<int>(U * c / grid) * unit;
+  r1 = (c == grid - 1) ? N : static_cast<int>(U * (c + 1) / grid) * unit;
 }
 
 // timeline (TRACE_B200_MEGA_TIMING=1): [2 CTAs][layers][32] stamps of CTAs 0 and 77, then [gridDim][32] stamps of EVERY CTA for
@@ -355,22 +345,33 @@ __device__ __forceinline__ void stage_rms(__half* xs, int pitch, const uint2* sr
 // ---- weight stream: producer -----------------------------------------------------------------------------------
 // rows [vlo,vhi) of the tiles of [r0,r1) in (k-phase, tile, k-stage) order, one bulk copy per row per stage
 __device__ __forceinline__ void produce_matrix(const __half* __restrict__ W, int K, int KP, int KS, int r0, int r1, int vlo, int vhi,
-                                               const DsSmem& m, int stages, int& s, uint32_t& ph, const Watch& w) {
+                                               const DsSmem& m, int stages, int& s, uint32_t& ph, const Watch& w, bool k_outer) {
   const int lane = threadIdx.x & 31;
   const int pitch = KS + WS_PAD;
-  GvItems it;
-  it.init(K, KP, KS, r0, r1, vlo, vhi);
-  while (!it.done) {
-    const int tr0 = r0 + it.tile * GV_TILE;
+  auto put = [&](int tile, int kcol) {
+    const int tr0 = r0 + tile * GV_TILE;
     const int lo = max(tr0, vlo), hi = min(tr0 + GV_TILE, vhi);
     ds_mbar_wait(&m.empty[s], ph ^ 1, w, 31);
     if (lane == 0) mbar_expect_tx(&m.full[s], static_cast<uint32_t>(hi - lo) * KS * 2);
     __syncwarp();
     const int row = tr0 + lane;
     if (lane < GV_TILE && row >= lo && row < hi)
-      bulk_g2s(m.ws + static_cast<size_t>(s) * DS_STAGE_HALVES + static_cast<size_t>(lane) * pitch, W + static_cast<size_t>(row) * K + it.k0 + it.ks,
-               KS * 2, &m.full[s]);
+      bulk_g2s(m.ws + static_cast<size_t>(s) * DS_STAGE_HALVES + static_cast<size_t>(lane) * pitch, W + static_cast<size_t>(row) * K + kcol, KS * 2,
+               &m.full[s]);
     if (++s == stages) { s = 0; ph ^= 1; }
+  };
+  if (k_outer) {
+    // (k-stage, tile) order: the consumers multiply a 1024-column chunk of the input for all their tiles as soon as that
+    // chunk exists (consume_korder), so a late producer of the previous phase only delays the chunk it produces
+    const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
+    for (int kcol = 0; kcol < K; kcol += KS)
+      for (int tile = 0; tile < ntile; ++tile) put(tile, kcol);
+    return;
+  }
+  GvItems it;
+  it.init(K, KP, KS, r0, r1, vlo, vhi);
+  while (!it.done) {
+    put(it.tile, it.k0 + it.ks);
     it.next();
   }
 }
@@ -461,6 +462,72 @@ __device__ __forceinline__ void consume_tiles(const DsSmem& m, const __half* xs,
     }
     ds_flush_tile<NBC>(pt, c, g, t, add);
   }
+}
+
+// O / down projection at batch <= 2, k-outer: for every KS-column chunk of the input, in order, every warp polls ITS OWN K slice
+// of the chunk out of the exchange buffer (one 16-byte poll per lane and batch row: KS/8 = 128 elements per warp), stages it
+// for its own MMA fragments (no CTA barrier -- nobody else reads that slice) and multiplies it into the accumulators of all
+// the CTA's row tiles.  The poll of chunk j+1 is in flight while chunk j is multiplied.  Tiles: ceil(rows/16) <= 3.
+template <int NBC>
+__device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src_ll, int row_units, int K, int KS, int ntile, int B, unsigned epoch,
+                                               int stages, int& rs, uint32_t& rph, const Watch& w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ksw = KS / GV_WARPS;                   // this warp's columns of a chunk
+  const int nch = ksw / 32;
+  const int wpitch = KS + WS_PAD;
+  const int xpitch = K + XS_PAD;
+  const bool xok = g < B;
+  const bool full = nch == 4;
+  const bool mine = 4 * lane < ksw;                // lanes that poll (all 32 when KS = 1024)
+  const uint4* s4 = reinterpret_cast<const uint4*>(src_ll);
+  const int row4 = row_units >> 1;
+  float c[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+  uint4 nxt[NBC];
+  auto issue = [&](int kcol) {
+#pragma unroll
+    for (int b = 0; b < NBC; ++b)
+      if (mine && b < B) nxt[b] = ll_ld16(s4 + static_cast<size_t>(b) * row4 + ((kcol + warp * ksw) >> 2) + lane);
+  };
+  issue(0);
+  for (int kcol = 0; kcol < K; kcol += KS) {
+#pragma unroll
+    for (int b = 0; b < NBC; ++b) {
+      if (mine && b < B) {
+        const uint4* a = s4 + static_cast<size_t>(b) * row4 + ((kcol + warp * ksw) >> 2) + lane;
+        unsigned spins = 0;
+        while (nxt[b].y != epoch || nxt[b].w != epoch) {
+          ds_repoll(w, spins, 23);
+          nxt[b] = ll_ld16(a);
+        }
+        *reinterpret_cast<uint2*>(m.xs + static_cast<size_t>(b) * xpitch + kcol + warp * ksw + 4 * lane) = make_uint2(nxt[b].x, nxt[b].z);
+      }
+    }
+    __syncwarp();
+    if (kcol + KS < K) issue(kcol + KS);
+    const __half* xp = m.xs + g * xpitch + kcol + warp * ksw + t * 8;
+#pragma unroll
+    for (int tile = 0; tile < 3; ++tile) {
+      if (tile < ntile) {
+        ds_mbar_wait(&m.full[rs], rph, w, 32);
+        const __half* wa = m.ws + static_cast<size_t>(rs) * DS_STAGE_HALVES + static_cast<size_t>(g) * wpitch + warp * ksw + t * 8;
+        const __half* wb = wa + 8 * wpitch;
+        uint32_t wr[32];
+        if (full) ds_load_item<true>(wr, wa, wb, nch);
+        else ds_load_item<false>(wr, wa, wb, nch);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&m.empty[rs]);
+        if (full) ds_mma_item<true>(c[tile], wr, xp, xok, nch);
+        else ds_mma_item<false>(c[tile], wr, xp, xok, nch);
+        if (++rs == stages) { rs = 0; rph ^= 1; }
+      }
+    }
+  }
+#pragma unroll
+  for (int tile = 0; tile < 3; ++tile)
+    if (tile < ntile) ds_flush_tile<NBC>(m.s_part + (static_cast<size_t>(tile) * GV_WARPS + warp) * (GV_TILE * NBC), c[tile], g, t, false);
 }
 
 // epilogue of tiles [t0,t1): kind 0 store, 1 residual add (residual rows live in shared memory), 2 SwiGLU pairs.
@@ -560,7 +627,7 @@ __device__ __forceinline__ void attn_item(const DsParams& p, const DsLayer& L, c
     const int grid = gridDim.x, qkvw = p.qkvw;
     wait_flags(p.fq, ep_qkv, grid, [&](int c) {
       int a0, a1;
-      rows_of_cta(p.cum, qkvw, 2, c, grid, a0, a1);
+      rows_of_cta(qkvw, 2, c, grid, a0, a1);
       bool need = a0 < q0 + DS_G * DS_HD && a1 > q0;
       if (split == 0) need = need || (a0 < k0r + DS_HD && a1 > k0r) || (a0 < v0r + DS_HD && a1 > v0r);
       return need;
@@ -990,13 +1057,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
     }
     fence_barrier_init();
   }
-  int vid = blockIdx.x;
-  if (p.cum != nullptr) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (smid >= gridDim.x) ds_die(p.err, 61);                   // SM ids are not 0..gridDim-1 here: run with TRACE_B200_BALANCE=0
-    vid = static_cast<int>(smid);
-  }
+  const int vid = blockIdx.x;
   attn_ctl_init(p, &s_ctl, vid);                                // contains __syncthreads
   const int ncta = gridDim.x;
   int ulo = 0x7fffffff, uhi = 0;
@@ -1015,10 +1076,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
       const DsLayer& L = s_layers[type == 4 ? 0 : l];
       const PhaseGeo g = phase_geo(p, type);
       int r0, r1;
-      rows_of_cta(p.cum, g.N, g.unit, vid, ncta, r0, r1);
+      rows_of_cta(g.N, g.unit, vid, ncta, r0, r1);
       const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
       const __half* W = type == 0 ? L.qkv_w : type == 1 ? L.o_w : type == 2 ? L.gateup_w : type == 3 ? L.down_w : p.head_w;
-      if (vlo < vhi) produce_matrix(W, g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, w);
+      if (vlo < vhi) produce_matrix(W, g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, w, NB <= 2 && (type == 1 || type == 3));
       if (type == 0 && s_ctl.valid) {
         // the K/V pages of this CTA's attention work item: cached rows do not depend on this step, so they queue right
         // behind the QKV weights and are in shared memory before q exists
@@ -1042,7 +1103,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
   int rs = 0;
   uint32_t rph = 0;
   int xr0, xr1;
-  rows_of_cta(p.cum, p.H, 2, vid, ncta, xr0, xr1);
+  rows_of_cta(p.H, 2, vid, ncta, xr0, xr1);
   // residual rows of this CTA (the O and down projections share one row partition): kept in shared memory for the whole step
   for (int i = threadIdx.x; i < p.B * DS_RES_PITCH; i += GV_CONS) {
     const int n = i / DS_RES_PITCH, r = i % DS_RES_PITCH;
@@ -1052,7 +1113,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
   constexpr int NLD = NB <= 2 ? 8 : 16;     // (16 polls in flight per thread make ptxas spill the batch-1 kernel: a spill is an L2 round trip here)
   constexpr bool DENSE = NB >= 4;
   const int xpitch_h = p.H + XS_PAD;
-  unsigned long long t_phase = 0, t_stream = 0;      // thread 0: time from "input staged" to "last stage consumed", summed over the phases
   const auto all_ctas = [](int) { return true; };
 
   for (int seq = 0; seq < nseq; ++seq) {
@@ -1061,7 +1121,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
     const PhaseGeo g = phase_geo(p, type);
     const unsigned epl = ep0 + 8u * static_cast<unsigned>(l);
     int r0, r1;
-    rows_of_cta(p.cum, g.N, g.unit, vid, ncta, r0, r1);
+    rows_of_cta(g.N, g.unit, vid, ncta, r0, r1);
     const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
     const int ntile = (r1 - r0 + GV_TILE - 1) / GV_TILE;
     int tlo = 0, thi = 0;
@@ -1084,6 +1144,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
         const bool dense = seq == 0;
         stage_rms<NLD>(m.xs, xpitch_h, dense ? nullptr : p.x_ll, p.x, p.B, p.H, gm, p.eps, m.s_red, dense ? 0u : epx, w);
       }
+      if (!DENSE && !pro) {
+        // O / down projection, flag-in-data mode: k-outer, chunks multiplied as they arrive (consume_korder)
+        stamp(p, l, 10 + type * 2);
+        consume_korder<NB>(m, type == 1 ? p.attn_ll : p.act_ll, (type == 1 ? p.qd : p.ffn) >> 1, g.K, g.KS, ntile, p.B, type == 1 ? epl + 3 : epl + 5,
+                           p.stages, rs, rph, w);
+        cons_sync();
+        stamp(p, l, 24 + type);
+        epilogue_ll<NB, false>(m, r0, r1, 0, ntile, p.B, 1, p.x_ll, p.xd, p.H >> 1, type == 1 ? epl + 4 : epl + 6, s_res);
+      }
       const int nkp = g.K / g.KP;
       const int xs_buf = p.B * (g.KP + XS_PAD);          // halves per staging buffer of a k-phase
       // dense mode: the next k-phase's activations are in flight (registers) while this one is consumed.  Batch 8: k-phases of
@@ -1103,20 +1172,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
           dense_store<PF>(pre, m.xs, g.KP + XS_PAD, p.B, g.KP);
         }
       }
-      for (int k0 = 0, kpi = 0; k0 < g.K; k0 += g.KP, ++kpi) {
+      for (int k0 = 0, kpi = 0; k0 < g.K && (DENSE || pro); k0 += g.KP, ++kpi) {
         const __half* xcur = m.xs;
-        if (!pro && !DENSE) {
-          if (k0 > 0) cons_sync();
-          if (type == 1) stage_ll<NLD>(m.xs, g.KP + XS_PAD, p.attn_ll, p.qd >> 1, p.B, k0, g.KP, epl + 3, w);
-          else stage_ll<NLD>(m.xs, g.KP + XS_PAD, p.act_ll, p.ffn >> 1, p.B, k0, g.KP, epl + 5, w);
-        }
         cons_sync();                                      // staged activations visible; every warp is done with the previous k-phase
         if constexpr (DENSE) if (!pro) {
           if (DBUF) xcur = m.xs + (kpi & 1) * xs_buf;
           if (k0 + g.KP < g.K) dense_issue<PF>(pre, type == 1 ? p.attnd : p.actd, g.K, p.B, k0 + g.KP, g.KP);
         }
         if (k0 == 0) stamp(p, l, 10 + type * 2);
-        if (k0 == 0 && type < 4 && threadIdx.x == 0) t_phase = gtimer();
         const int gt = nkp > 1 ? ntile : p.group_tiles;
         for (int t0 = 0; t0 < ntile; t0 += gt) {
           const int t1 = min(ntile, t0 + gt);
@@ -1130,7 +1193,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
           }
           cons_sync();
           if (t1 == ntile) stamp(p, l, 24 + type);
-          if (t1 == ntile && type < 4 && threadIdx.x == 0) t_stream += gtimer() - t_phase;
           if (type == 0) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 0, p.qkv_ll, p.qkvd, p.qkvw >> 1, epl + 1, s_res);
           else if (type == 1) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 1, p.x_ll, p.xd, p.H >> 1, epl + 4, s_res);
           else if (type == 2) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 2, p.act_ll, p.actd, p.ffn >> 1, epl + 5, s_res);
@@ -1193,7 +1255,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
       }
     }
   }
-  if (threadIdx.x == 0 && p.stream_ns != nullptr && p.layers > 0) p.stream_ns[vid] += static_cast<unsigned>(t_stream);   // the host reads and clears it
   if (vid == 0) {
     cons_sync();
     finalize_step(p, ncta, ep0 + 8u * static_cast<unsigned>(p.layers) + 1, s_hlo, s_hhi, w);
@@ -1370,7 +1431,7 @@ int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream) {
   p.cos_tab = a.cos_tab; p.sin_tab = a.sin_tab; p.block_table = a.block_table; p.max_pages = a.max_pages;
   p.logits_out = a.logits_out; p.samp_logits = a.samp_logits;
   p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
-  p.st = a.st; p.epoch_ctr = a.epoch_ctr; p.err = a.err; p.advance = a.advance; p.dbg = a.dbg; p.poll_sleep_ns = a.poll_sleep_ns; p.cum = a.cum; p.stream_ns = a.stream_ns; p.watchdog_ms = a.watchdog_ms > 0 ? a.watchdog_ms : 4000;
+  p.st = a.st; p.epoch_ctr = a.epoch_ctr; p.err = a.err; p.advance = a.advance; p.dbg = a.dbg; p.poll_sleep_ns = a.poll_sleep_ns; p.watchdog_ms = a.watchdog_ms > 0 ? a.watchdog_ms : 4000;
   size_t smem = 0;
   if (ds_plan(a, p, &smem)) return 1;
   int rc;

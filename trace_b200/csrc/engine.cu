@@ -106,11 +106,6 @@ struct trace_b200_ctx {
   bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
   // fused decode step, v2 (decode_stream.cu)
   int poll_sleep_ns = 0, watchdog_ms = 4000;
-  int balance = 1;                // TRACE_B200_BALANCE=0: equal rows per CTA instead of rows proportional to the SM's measured bandwidth share
-  float* d_cum = nullptr;
-  unsigned* d_stream_ns = nullptr;
-  std::vector<float> sm_share;    // current row share per SM id, relative to uniform
-  int balance_rounds = 0;         // feedback rounds applied so far (stops at kBalanceRounds)
   int decode_v = 2;               // TRACE_B200_DECODE=1 selects the round-1 kernel (decode_mega.cu) with its own KV layout
   int cooperative = 1;
   void* d_exchange = nullptr;
@@ -288,7 +283,6 @@ int allocate_all(trace_b200_ctx* ctx) {
     ctx->cooperative = env_int("TRACE_B200_COOP", 0, 1, 1);
     if (ctx->decode_v == 2) ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
     ctx->poll_sleep_ns = env_int("TRACE_B200_POLL_SLEEP", 0, 5000, 0);
-    ctx->balance = env_int("TRACE_B200_BALANCE", 0, 1, 1);
     ctx->watchdog_ms = env_int("TRACE_B200_WATCHDOG_MS", 1, 3600000, 4000);    // compute-sanitizer runs need minutes
   }
   // ---- KV pool ----
@@ -557,7 +551,7 @@ DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* 
   a.exchange = ctx->d_exchange; a.cos_tab = ctx->rope_cos; a.sin_tab = ctx->rope_sin; a.block_table = ctx->d_block_table;
   a.logits_out = logits_out; a.samp_logits = ctx->d_samp_logits; a.embed = ctx->embed; a.time_tab = ctx->time_tab;
   a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab; a.st = ctx->sst; a.epoch_ctr = ctx->d_epoch; a.err = ctx->d_err;
-  a.advance = layers_run > 0 ? 1 : 0; a.cooperative = ctx->cooperative; a.max_stages = ctx->max_stages; a.poll_sleep_ns = ctx->poll_sleep_ns; a.watchdog_ms = ctx->watchdog_ms; a.cum = ctx->d_cum; a.stream_ns = ctx->d_stream_ns; a.dbg = ctx->d_dbg;
+  a.advance = layers_run > 0 ? 1 : 0; a.cooperative = ctx->cooperative; a.max_stages = ctx->max_stages; a.poll_sleep_ns = ctx->poll_sleep_ns; a.watchdog_ms = ctx->watchdog_ms; a.dbg = ctx->d_dbg;
   return a;
 }
 
@@ -565,47 +559,6 @@ DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* 
 int decode_step_v2(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, cudaStream_t s) {
   const DecodeStreamArgs a = stream_args(ctx, B, layers_run, logits_out);
   RUN(decode_stream_step(a, s));
-  return 0;
-}
-
-// Bandwidth-balanced row partition, closed loop: the last launch reported how long every SM spent in its streaming phases;
-// SMs that took longer than average get proportionally fewer rows (damped, clamped to +-12 % of uniform).  A few rounds
-// during the first bursts of a context's life are enough: the imbalance is a fixed property of the SM's position.
-constexpr int kBalanceRounds = 8;
-int rebalance(trace_b200_ctx* ctx, cudaStream_t s) {
-  if (ctx->d_cum == nullptr || ctx->balance_rounds >= kBalanceRounds) return 0;
-  const int n = ctx->num_sms;
-  std::vector<unsigned> ns(n);
-  TB_CUDA(cudaMemcpyAsync(ns.data(), ctx->d_stream_ns, n * 4, cudaMemcpyDeviceToHost, s));
-  TB_CUDA(cudaStreamSynchronize(s));
-  double mean = 0;
-  for (int i = 0; i < n; ++i) {
-    if (ns[i] == 0) return 0;                       // an SM id never seen (or a head-only launch): leave the partition alone
-    mean += ns[i];
-  }
-  mean /= n;
-  TB_CUDA(cudaMemsetAsync(ctx->d_stream_ns, 0, n * 4, s));    // the kernel accumulates over the launches of a burst
-  if (mean < 2e6) return 0;                         // too short to measure (parity-test models): keep equal rows
-  double wsum = 0;
-  std::vector<double> wgt(n);
-  for (int i = 0; i < n; ++i) {
-    double r = ctx->sm_share[i] * (1.0 + 0.7 * (mean / ns[i] - 1.0));
-    if (r > 1.12) r = 1.12;
-    if (r < 0.88) r = 0.88;
-    wgt[i] = r;
-    wsum += r;
-  }
-  std::vector<float> cum(n + 1);
-  double acc = 0;
-  for (int i = 0; i < n; ++i) {
-    cum[i] = static_cast<float>(acc / wsum);
-    ctx->sm_share[i] = static_cast<float>(wgt[i] * n / wsum);
-    acc += wgt[i];
-  }
-  cum[n] = 1.0f;
-  TB_CUDA(cudaMemcpyAsync(ctx->d_cum, cum.data(), cum.size() * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaStreamSynchronize(s));                // `cum` is a stack vector
-  ++ctx->balance_rounds;
   return 0;
 }
 
@@ -698,7 +651,6 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
       ctx->launches_since_reset += burst;
       if (poll_done()) return 1;
       if (done) break;
-      if (rebalance(ctx, s)) return 1;
     }
   }
   TB_CUDA(cudaEventRecord(ctx->ev_t1, s));
@@ -802,14 +754,6 @@ int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
       ctx->d_layer_table = dt;
     }
     TB_CUDA(cudaMemcpy(ctx->d_layer_table, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice));
-  }
-  if (ctx->decode_v == 2 && ctx->balance && ctx->d_cum == nullptr) {
-    // rows per SM start uniform and are adapted from the kernel's own per-SM streaming times (rebalance below)
-    ctx->sm_share.assign(ctx->num_sms, 1.0f);
-    std::vector<float> cum(ctx->num_sms + 1);
-    for (int i = 0; i <= ctx->num_sms; ++i) cum[i] = static_cast<float>(i) / ctx->num_sms;
-    if (dalloc(ctx, &ctx->d_cum, cum.size()) || dalloc(ctx, &ctx->d_stream_ns, ctx->num_sms, true)) return 1;
-    TB_CUDA(cudaMemcpy(ctx->d_cum, cum.data(), cum.size() * 4, cudaMemcpyHostToDevice));
   }
   TB_CUDA(cudaDeviceSynchronize());
   ctx->finalized = true;
@@ -1028,15 +972,6 @@ int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int 
   ctx->forced_n = n;
   return 0;
 }
-
-int trace_b200_sm_shares(trace_b200_ctx* ctx, float* out, int capacity) {
-  TB_CHECK(ctx != nullptr && out != nullptr, "null argument");
-  const int n = ctx->d_cum != nullptr ? static_cast<int>(ctx->sm_share.size()) : 0;
-  TB_CHECK(capacity >= n, "buffer too small");
-  for (int i = 0; i < n; ++i) out[i] = ctx->sm_share[i];
-  return 0;
-}
-int trace_b200_sm_share_count(trace_b200_ctx* ctx) { return (ctx != nullptr && ctx->d_cum != nullptr) ? static_cast<int>(ctx->sm_share.size()) : 0; }
 
 int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8) {
   TB_CHECK(ctx != nullptr && out8 != nullptr, "null argument");

@@ -164,8 +164,6 @@ struct DecodeStreamArgs {
   int* err;                      // device error word written by the kernel's watchdog before it traps
   int advance;                   // 0: head-only launch on the prefill's last hidden state (layers must be 0), 1: a decoder pass
   int cooperative, max_stages, poll_sleep_ns, watchdog_ms;
-  const float* cum;              // [num_sms+1] cumulative row share per SM id, or null = equal rows per CTA (by blockIdx)
-  unsigned* stream_ns;           // [num_sms] out (by SM id): nanoseconds this launch spent in its streaming phases, or null
   unsigned long long* dbg;
 };
 int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream);

@@ -22,7 +22,7 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_sm_share_count", "trace_b200_sm_shares", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
     "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
 ]
 
@@ -70,8 +70,6 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_set_sampling.argtypes = [vp, i32, f32, i32, ctypes.c_uint64]
     lib.trace_b200_set_forced_ids.argtypes = [vp, ctypes.POINTER(i64), i32, i32]
     lib.trace_b200_decode_plan.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_int32)]
-    lib.trace_b200_sm_share_count.argtypes = [vp]
-    lib.trace_b200_sm_shares.argtypes = [vp, ctypes.POINTER(f32), i32]
     lib.trace_b200_launch_count.argtypes = [vp]
     lib.trace_b200_launch_count.restype = i64
     lib.trace_b200_last_decode_timing.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
@@ -238,15 +236,6 @@ class Engine:
         _check(self.lib.trace_b200_decode_plan(self._h, B, context_len, out))
         keys = ("nsplit", "ncomb", "kv_tiles_per_item", "kp_down", "ks_down", "stages", "group_tiles", "smem_bytes")
         return dict(zip(keys, list(out)))
-
-    def sm_shares(self) -> List[float]:
-        """Measured HBM bandwidth share per SM id relative to uniform ([] when the balanced row partition is off)."""
-        n = int(self.lib.trace_b200_sm_share_count(self._h))
-        if n == 0:
-            return []
-        buf = (ctypes.c_float * n)()
-        _check(self.lib.trace_b200_sm_shares(self._h, buf, n))
-        return list(buf)
 
     @property
     def launch_count(self) -> int:
