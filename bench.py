@@ -487,8 +487,7 @@ def run_b200(args):
                    "clips_per_step": world, "frames": T, "prompt_len": L_TEXT, "prefill_len": S, "max_new_tokens": max_new,
                    "weights": args.weights + " synthetic fp16 (seed 0)", "tokens_per_event": TOKENS_PER_EVENT,
                    "api": "TraceMistralForCausalLM.generate" if world == 1 else "trace_b200.parallel.generate_sharded (local frame slices)",
-                   "decode_path": ("round-1 fused decode kernel" if os.environ.get("TRACE_B200_DECODE") == "1" else
-                                   "streamed decode step: one cooperative kernel per token (CUDA graph), weights + K/V pages through one TMA ring"),
+                   "decode_path": "fused decode step: one cooperative kernel per token (CUDA graph), weights + K/V pages through one TMA ring",
                    "parallelism": "1 GPU" if world == 1 else f"frame-sharded ViT x{world} + 1 all-gather, replicated LLM, 1 clip/GPU",
                    "l2_policy": "per-step working set (14.5 GB weights) >> 126 MB L2, no flush needed",
                    "weight_init_s": round(t_load, 1)},

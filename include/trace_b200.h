@@ -122,7 +122,8 @@ int64_t trace_b200_weight_bytes(trace_b200_ctx* ctx);
 int trace_b200_last_decode_timing(trace_b200_ctx* ctx, float* ms_out, int* steps_out);
 
 /* debugging aid: %globaltimer stamps (and a few counters) of the last fused decode step, [2 CTAs][layers][32 slots]
- * (needs TRACE_B200_MEGA_TIMING=1 in the environment when the context is created; tools/profile_step.py decodes it). */
+ * (needs TRACE_B200_MEGA_TIMING=1 in the environment when the context is created; tools/profile_step.py decodes it).  A capacity
+ * of 2*layers*32 + SMs*32 also returns the stamps of EVERY CTA for the middle layer (slot 31 = SM id). */
 int trace_b200_debug_timeline(trace_b200_ctx* ctx, uint64_t* out_host, int capacity);
 
 /* Frame pre-processing on the device: what process_video does per decoded frame on the host (trace/mm_utils.py:424-462):
@@ -144,14 +145,9 @@ int trace_b200_op_gemm(const void* A, int lda, const void* W, int ldw, void* out
 int trace_b200_op_layernorm(const void* x, const void* w, const void* b, float eps, void* out, int rows, int D,
                             void* stream);
 int trace_b200_op_rmsnorm(const void* x, const void* w, float eps, void* out, int rows, int D, void* stream);
-int trace_b200_op_attention(const void* q, const void* k, const void* v, void* o, int seqlen, int q_stride,
-                            int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride,
-                            int heads, int group, int batch, int head_dim, int causal, float scale, void* stream);
 /* tcgen05 / TMEM attention over a fused [batch*seqlen, (heads+2*kv_heads)*head_dim] activation */
 int trace_b200_op_attention_tc(const void* qkv, int width, void* o, int seqlen, int heads, int kv_heads, int head_dim, int causal,
                                int batch, float scale, void* stream);
-int trace_b200_op_gemv(const void* W, const void* x, void* out, int B, int N, int K, int pro, const void* gamma,
-                       float eps, int epi, void* stream);
 
 #ifdef __cplusplus
 }

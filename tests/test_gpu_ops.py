@@ -75,7 +75,7 @@ def test_gemm_wide_tiles_all_epilogues():
 
 def test_norms():
     from trace_b200 import engine as E
-    for D in (128, 192, 1024, 4096):
+    for D in (128, 192, 1024, 4096):     # 128 / 192: one-CTA-per-row kernel; 1024 / 4096: warp-per-row kernel
         x, w, b = _rand((333, D), 2.0, 7), (1 + 0.1 * _rand((D,), 1.0, 8).float()).half(), _rand((D,), 0.1, 9)
         if D <= 1024:
             want = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5)
@@ -88,11 +88,10 @@ def test_norms():
 @pytest.mark.parametrize("B,S,heads,kvh,hd,causal", [(3, 577, 2, 2, 64, False), (2, 17, 2, 2, 64, False),
                                                      (2, 200, 32, 8, 128, True), (1, 67, 32, 8, 128, True),
                                                      (1, 1000, 8, 2, 128, True)])
-@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
-def test_attention(B, S, heads, kvh, hd, causal, impl):
+def test_attention(B, S, heads, kvh, hd, causal):
     from trace_b200 import engine as E
     qkv = _rand((B, S, (heads + 2 * kvh) * hd), 1.0, 11)
-    out = (E.op_attention if impl == "mma_sync" else E.op_attention_tc)(qkv, heads, kvh, hd, causal)
+    out = E.op_attention_tc(qkv, heads, kvh, hd, causal)
     torch.cuda.synchronize()
     q = qkv[..., : heads * hd].float().view(B, S, heads, hd).transpose(1, 2)
     k = qkv[..., heads * hd: (heads + kvh) * hd].float().view(B, S, kvh, hd).transpose(1, 2)
@@ -129,25 +128,6 @@ def test_attention_tcgen05_lazy_rescale(S, hd, causal):
         s_ = s_.masked_fill(torch.triu(torch.ones(S, S, device="cuda", dtype=torch.bool), 1), float("-inf"))
     want = (torch.softmax(s_, -1) @ v).transpose(1, 2).reshape(B, S, heads * hd)
     _close(out, want, 1e-2, 1e-2, f"attention tcgen05 lazy rescale S{S} d{hd}")
-
-
-@pytest.mark.parametrize("B,N,K", [(1, 4096, 4096), (3, 6144, 4096), (8, 4096, 14336), (2, 512, 256), (1, 4096, 512)])
-def test_gemv(B, N, K):
-    from trace_b200 import engine as E
-    w, x = _rand((N, K), 0.02, 21), _rand((B, K), 1.0, 22)
-    want = x.float() @ w.float().t()
-    _close(E.op_gemv(w, x), want, 2e-3, 2e-3 * float(want.abs().max()), "gemv plain")
-    res = _rand((B, N), 1.0, 23)
-    out = res.clone()
-    E.op_gemv(w, x, epi=1, out=out)
-    _close(out, want + res.float(), 2e-3, 4e-3, "gemv residual")
-    _close(E.op_gemv(w, x, epi=2), torch.nn.functional.silu(want[:, 0::2]) * want[:, 1::2], 2e-3, 2e-3, "gemv swiglu")
-    if K <= 4096:
-        gamma = (1 + 0.1 * _rand((K,), 1.0, 24).float()).half()
-        xf = x.float()
-        xn = gamma.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).half().float()
-        wantn = xn.half().float() @ w.float().t()
-        _close(E.op_gemv(w, x, gamma=gamma, eps=1e-5), wantn, 2e-3, 2e-3 * float(wantn.abs().max()), "gemv rmsnorm")
 
 
 @pytest.mark.parametrize("h,w,pad", [(360, 640, True), (480, 270, True), (336, 336, True), (240, 426, False), (1080, 1920, True)])

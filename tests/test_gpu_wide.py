@@ -5,8 +5,6 @@ These are the shapes BASELINE configs 2-5 run per layer: the head partition over
 projection of the batch-4 / batch-8 decode step, several K/V page tiles per attention work item, a context beyond 2304
 positions.  Every decode step is teacher-forced with the reference's ids, so the per-step logits stay comparable after an
 fp16 tie; the free-running CUDA-graph loop is then compared id by id (ties below the logit tolerance excepted)."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -15,7 +13,6 @@ from trace_b200 import synth
 from tests.util import WIDE_CASES, load_case, ranges, row_heads0, compare_ids_with_margin
 
 pytestmark = pytest.mark.gpu
-V1 = os.environ.get("TRACE_B200_DECODE") == "1"      # round-1 kernel (A/B runs): no teacher forcing, no plan introspection
 
 LOGIT_TOL = 0.08     # |logit| up to ~16 (fp16 step 2^-6 = 0.016 there), fp16 activations through 2 full-width layers
 FEAT_TOL = 0.03      # relative to max |x| of the tensor
@@ -64,26 +61,22 @@ def test_wide_case_against_reference_outputs(name):
     assert _rel(hn[:, ::7, ::s3], z["hid_sample"]) < FEAT_TOL, f"prefill hidden rel err {_rel(hn[:, ::7, ::s3], z['hid_sample'])}"
     assert _rel(hn[:, -1, :], z["hid_last"]) < FEAT_TOL
     # ---- the launch plan really is the full-size one ----
-    plan = {} if V1 else eng.decode_plan(B, S)
-    if B >= 4 and not V1:
-        assert plan["kp_down"] < d.ffn, f"batch {B}: the down projection must take the k-phased path ({plan})"
-    if name != "wide_b1" and not V1:
+    plan = eng.decode_plan(B, S)
+    assert plan["ks_down"] == 1024 and plan["stages"] >= 3, plan          # full 1024-column stages, as in the full-size model
+    if name != "wide_b1":
         assert plan["kv_tiles_per_item"] >= 2, f"{name}: attention work items must span several K/V page tiles ({plan})"
     # ---- teacher-forced decode: every step's active-head logits against the reference's top-8 ----
     heads = row_heads0(meta)
     ref_ids = torch.tensor(z["out_ids"], dtype=torch.int64)
     n_ref = ref_ids.shape[1]
     assert n_ref == max_new
-    out, logits = eng.decode(kv, list(heads), max_new, return_logits=True, forced_ids=None if V1 else ref_ids)
+    out, logits = eng.decode(kv, list(heads), max_new, return_logits=True, forced_ids=ref_ids)
     assert out.shape[1] == n_ref
     rg = ranges(d)
     worst, ties = 0.0, 0
     lg = logits.cpu()
-    dead = set()                                     # v1 only: rows that took the other side of an fp16 tie
     for s in range(n_ref):
         for b in range(B):
-            if b in dead:
-                continue
             h = int(z["step_heads"][s][b])
             lo, hi = rg[h]
             idx = torch.tensor(z["top_idx"][s][b])
@@ -99,8 +92,6 @@ def test_wide_case_against_reference_outputs(name):
                 margin = float(z["top_vals"][s][b][0] - z["top_vals"][s][b][1])
                 assert margin < LOGIT_TOL, f"{name} step {s} row {b}: got {int(out[b, s])} want {int(ref_ids[b, s])}, reference margin {margin}"
                 ties += 1
-                if V1:
-                    dead.add(b)
     print(f"{name}: {n_ref * B} steps, worst logit error {worst:.4g} (tol {LOGIT_TOL}), {ties} fp16 tie-breaks, plan {plan}")
     for sl in kv:
         eng.free_slot(sl)

@@ -17,7 +17,7 @@ for name, B, S, heads, kvh, hd, causal in (("vit", 32, 577, 16, 16, 64, False), 
     qkv = torch.randn(B, S, (heads + 2 * kvh) * hd, device="cuda").half()
     fl = 4.0 * B * heads * S * S * hd * (0.5 if causal else 1.0)
     outs = {}
-    for impl, fn in (("mma.sync", E.op_attention), ("tcgen05", E.op_attention_tc)):
+    for impl, fn in (("tcgen05", E.op_attention_tc),):
         outs[impl] = fn(qkv, heads, kvh, hd, causal)
         ms = timeit(lambda: fn(qkv, heads, kvh, hd, causal))
         print(f"attn {name:9s} {impl:9s} B={B} S={S} h={heads}/{kvh} d={hd}  {ms * 1e3:9.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s")

@@ -52,9 +52,7 @@ torch.cuda.synchronize()
 ms, st = model.engine.last_decode_timing()
 import hashlib
 print("ids", out.tolist()[0][:16], "sha", hashlib.sha1(str(out.tolist()).encode()).hexdigest()[:12])
-if os.environ.get("TRACE_B200_MEGA_TIMING") and os.environ.get("TRACE_B200_DECODE") == "1":
-    pass   # the round-1 kernel's stamp layout is no longer decoded here
-elif os.environ.get("TRACE_B200_MEGA_TIMING"):
+if os.environ.get("TRACE_B200_MEGA_TIMING"):
     # decode_stream.cu stamps per layer: 10+2*type staged, 24+type consumed, 11+2*type epilogue written (type 0 qkv, 1 o, 2 gate/up,
     # 3 down); attention: 20 q ready, 21 K/V tiles done, 22 partials written, 23 combine written, 3 phase left
     tl = model.engine.debug_timeline().double() / 1e3   # us
@@ -75,7 +73,7 @@ elif os.environ.get("TRACE_B200_MEGA_TIMING"):
         wait = sum(float((b - a_).mean()) for n, a_, b in seg if ".wait" in n)
         print(f"   cta{c}: streaming {stream:.2f} us, exchange waits {wait:.2f} us, attention compute {float((x[:, 23] - x[:, 20]).mean()):.2f} us, "
               f"epilogues {sum(float((b - a_).mean()) for n, a_, b in seg if n.endswith('.epi')):.2f} us")
-if os.environ.get("TRACE_B200_MEGA_TIMING") and os.environ.get("TRACE_B200_DECODE") != "1":
+if os.environ.get("TRACE_B200_MEGA_TIMING"):
     _, pc = model.engine.debug_timeline(per_cta=True)
     pc = pc.double()
     import json as _json

@@ -1,16 +1,14 @@
 #!/bin/bash
-# Round-2 GPU session 6: closed-loop balance, batch-4/8 staging changes, warp-per-row norms, tensor-map cache -- whole GPU suite,
-# then timelines at batch 1 / 4 / 8 and the bench line.
+# Round-2 GPU session 9: k-outer O / down projections in the dense (batch >= 4) mode too -- parity, timelines, bench with the batched configs.
 mkdir -p gpurun_out
 run() { local n=$1 t=$2; shift 2; timeout $t "$@" > gpurun_out/$n.log 2>&1; echo "$n exit $? | $(tail -1 gpurun_out/$n.log | cut -c1-300)"; }
 run smoke 240 python __graft_entry__.py smoke
 grep -q "smoke ok" gpurun_out/smoke.log || { tail -5 gpurun_out/smoke.log; exit 1; }
-run test_gpu_all 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider
-grep -E "FAILED|Error|assert" gpurun_out/test_gpu_all.log | head -20
-export TRACE_B200_MEGA_TIMING=1 MAXNEW=192
-bash tools/ab.sh bal:
-MAXNEW=160 BATCH=4 bash tools/ab.sh b4:
-MAXNEW=160 BATCH=8 bash tools/ab.sh b8:
+run test_gpu 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider
+grep -E "FAILED|Error|assert" gpurun_out/test_gpu.log | head -12
+export TRACE_B200_MEGA_TIMING=1 MAXNEW=96
+BATCH=4 bash tools/ab.sh b4:
+BATCH=8 bash tools/ab.sh b8:
 unset TRACE_B200_MEGA_TIMING
 timeout 900 python bench.py --steps 2 --warmup 2 --skip-cpu-baseline > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit $?"
 tail -3 gpurun_out/bench_full.err

@@ -181,40 +181,6 @@ __device__ __forceinline__ void stamp(const DsParams& p, int l, int k) {
 }
 
 // ---- activation staging ----------------------------------------------------------------------------------------
-// elements [k0, k0+KP) of each of the B rows of an exchange buffer -> xs[b][0..KP); NLD 16-byte polls in flight per thread
-template <int NLD>
-__device__ __forceinline__ void stage_ll(__half* xs, int pitch, const uint2* src, int row_units, int B, int k0, int KP, unsigned epoch,
-                                         const Watch& w) {
-  const int per_row = KP >> 2;
-  const int total = B * per_row;
-  const uint4* s4 = reinterpret_cast<const uint4*>(src) + (k0 >> 2);
-  const int row4 = row_units >> 1;
-  for (int base = 0; base < total; base += GV_CONS * NLD) {
-    uint4 v[NLD];
-#pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-      const int idx = base + i * GV_CONS + threadIdx.x;
-      if (idx < total) {
-        const int b = idx / per_row, j = idx - b * per_row;
-        v[i] = ll_ld16(s4 + static_cast<size_t>(b) * row4 + j);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-      const int idx = base + i * GV_CONS + threadIdx.x;
-      if (idx < total) {
-        const int b = idx / per_row, j = idx - b * per_row;
-        unsigned spins = 0;
-        while (v[i].y != epoch || v[i].w != epoch) {
-          ds_repoll(w, spins, 21);
-          v[i] = ll_ld16(s4 + static_cast<size_t>(b) * row4 + j);
-        }
-        *reinterpret_cast<uint2*>(xs + static_cast<size_t>(b) * pitch + 4 * j) = make_uint2(v[i].x, v[i].z);
-      }
-    }
-  }
-}
-
 // ---- dense exchange (batch >= 4) -----------------------------------------------------------------------------------
 // At batch 4..8 an activation vector is 32..460 KB per CTA per phase: doubling it with in-band flags and polling it unit by
 // unit costs more than it saves.  There the producers write plain fp16 and then release ONE epoch flag per CTA; consumers
@@ -240,34 +206,6 @@ __device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned epoch
   }
   cons_sync();
 }
-// elements [k0, k0+KP) of each of the B rows of a dense fp16 buffer: up to NLD 16-byte loads per thread, issued together
-template <int NLD>
-__device__ __forceinline__ void dense_issue(uint4 (&v)[NLD], const __half* src, int ld, int B, int k0, int KP) {
-  const int per_row = KP >> 3;
-  const int total = B * per_row;
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int idx = i * GV_CONS + threadIdx.x;
-    if (idx < total) {
-      const int b = idx / per_row, j = idx - b * per_row;
-      v[i] = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(b) * ld + k0) + j);
-    }
-  }
-}
-template <int NLD>
-__device__ __forceinline__ void dense_store(const uint4 (&v)[NLD], __half* xs, int pitch, int B, int KP) {
-  const int per_row = KP >> 3;
-  const int total = B * per_row;
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int idx = i * GV_CONS + threadIdx.x;
-    if (idx < total) {
-      const int b = idx / per_row, j = idx - b * per_row;
-      *reinterpret_cast<uint4*>(xs + static_cast<size_t>(b) * pitch + 8 * j) = v[i];
-    }
-  }
-}
-
 // RMSNorm weights of this thread's element groups: elements 4*(c*256 + tid) .. +3 for the row chunks c = 0..H/1024-1.
 // A weight: fetched BEFORE the activations are polled, so its HBM latency hides behind the wait.
 struct Gamma4 { uint2 g[4]; };
@@ -464,50 +402,81 @@ __device__ __forceinline__ void consume_tiles(const DsSmem& m, const __half* xs,
   }
 }
 
-// O / down projection at batch <= 2, k-outer: for every KS-column chunk of the input, in order, every warp polls ITS OWN K slice
-// of the chunk out of the exchange buffer (one 16-byte poll per lane and batch row: KS/8 = 128 elements per warp), stages it
-// for its own MMA fragments (no CTA barrier -- nobody else reads that slice) and multiplies it into the accumulators of all
-// the CTA's row tiles.  The poll of chunk j+1 is in flight while chunk j is multiplied.  Tiles: ceil(rows/16) <= 3.
-template <int NBC>
-__device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src_ll, int row_units, int K, int KS, int ntile, int B, unsigned epoch,
-                                               int stages, int& rs, uint32_t& rph, const Watch& w) {
+// O / down projection, k-outer: for every KS-column chunk of the input, in order, every warp fetches ITS OWN K slice of the
+// chunk (KS/8 = 128 columns per batch row), stages it in a warp-private buffer for its MMA fragments (no CTA barrier --
+// nobody else reads that slice) and multiplies it into the accumulators of all the CTA's row tiles (<= 3).  The fetch of
+// chunk j+1 is in flight while chunk j is multiplied, and a late producer of the previous phase only delays the chunk it
+// produces.
+//   batch <= 2 : the slice is polled out of the flag-in-data buffer (one 16-byte unit pair per lane and batch row);
+//   batch >= 4 : lanes acquire the epoch flags of the producer CTAs of the chunk (`need(c, kcol)`), then the warp loads its slice
+//                of the dense buffer with 16-byte loads.
+template <int NBC, bool DENSE, typename Need>
+__device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src_ll, const __half* src_d, const unsigned* flags, Need need, int ncta,
+                                               int K, int KS, int ntile, int B, unsigned epoch, int stages, int& rs, uint32_t& rph, const Watch& w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ksw = KS / GV_WARPS;                   // this warp's columns of a chunk
   const int nch = ksw / 32;
   const int wpitch = KS + WS_PAD;
-  const int xpitch = K + XS_PAD;
+  const int spitch = ksw + XS_PAD;                 // warp-private slice buffer: [NBC rows][ksw + pad]
+  __half* slice = m.xs + static_cast<size_t>(warp) * NBC * spitch;
   const bool xok = g < B;
   const bool full = nch == 4;
-  const bool mine = 4 * lane < ksw;                // lanes that poll (all 32 when KS = 1024)
-  const uint4* s4 = reinterpret_cast<const uint4*>(src_ll);
-  const int row4 = row_units >> 1;
   float c[3][4];
 #pragma unroll
   for (int i = 0; i < 3; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
-  uint4 nxt[NBC];
+  constexpr int NL = DENSE ? (NBC + 1) / 2 : NBC;  // 16-byte loads per lane per chunk
+  uint4 nxt[NL];
+  const int l16 = ksw >> 3;                        // dense: 16-byte loads per row of the slice (16 when KS = 1024)
   auto issue = [&](int kcol) {
+    if (DENSE) {
+      // producers of this chunk: every lane polls the flags c = lane, lane+32, ... it is responsible for
+      for (int cta = lane; cta < ncta; cta += 32) {
+        if (need(cta, kcol)) {
+          unsigned spins = 0;
+          while (ld_acquire_u32(flags + cta) != epoch) ds_repoll(w, spins, 23);
+        }
+      }
+      __syncwarp();
 #pragma unroll
-    for (int b = 0; b < NBC; ++b)
-      if (mine && b < B) nxt[b] = ll_ld16(s4 + static_cast<size_t>(b) * row4 + ((kcol + warp * ksw) >> 2) + lane);
+      for (int i = 0; i < NL; ++i) {
+        const int idx = lane + 32 * i, b = idx / l16, j = idx - b * l16;
+        if (b < B) nxt[i] = __ldcg(reinterpret_cast<const uint4*>(src_d + static_cast<size_t>(b) * K + kcol + warp * ksw) + j);
+      }
+    } else {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src_ll);
+#pragma unroll
+      for (int b = 0; b < NL; ++b)
+        if (4 * lane < ksw && b < B) nxt[b] = ll_ld16(s4 + static_cast<size_t>(b) * (K >> 2) + ((kcol + warp * ksw) >> 2) + lane);
+    }
   };
   issue(0);
   for (int kcol = 0; kcol < K; kcol += KS) {
+    __syncwarp();                                  // every lane is done with the previous chunk's fragments
+    if (DENSE) {
 #pragma unroll
-    for (int b = 0; b < NBC; ++b) {
-      if (mine && b < B) {
-        const uint4* a = s4 + static_cast<size_t>(b) * row4 + ((kcol + warp * ksw) >> 2) + lane;
-        unsigned spins = 0;
-        while (nxt[b].y != epoch || nxt[b].w != epoch) {
-          ds_repoll(w, spins, 23);
-          nxt[b] = ll_ld16(a);
+      for (int i = 0; i < NL; ++i) {
+        const int idx = lane + 32 * i, b = idx / l16, j = idx - b * l16;
+        if (b < B) *reinterpret_cast<uint4*>(slice + b * spitch + 8 * j) = nxt[i];
+      }
+    } else {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src_ll);
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        if (4 * lane < ksw && b < B) {
+          const uint4* a = s4 + static_cast<size_t>(b) * (K >> 2) + ((kcol + warp * ksw) >> 2) + lane;
+          unsigned spins = 0;
+          while (nxt[b].y != epoch || nxt[b].w != epoch) {
+            ds_repoll(w, spins, 23);
+            nxt[b] = ll_ld16(a);
+          }
+          *reinterpret_cast<uint2*>(slice + b * spitch + 4 * lane) = make_uint2(nxt[b].x, nxt[b].z);
         }
-        *reinterpret_cast<uint2*>(m.xs + static_cast<size_t>(b) * xpitch + kcol + warp * ksw + 4 * lane) = make_uint2(nxt[b].x, nxt[b].z);
       }
     }
     __syncwarp();
     if (kcol + KS < K) issue(kcol + KS);
-    const __half* xp = m.xs + g * xpitch + kcol + warp * ksw + t * 8;
+    const __half* xp = slice + g * spitch + t * 8;
 #pragma unroll
     for (int tile = 0; tile < 3; ++tile) {
       if (tile < ntile) {
@@ -1079,7 +1048,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
       rows_of_cta(g.N, g.unit, vid, ncta, r0, r1);
       const int vlo = type == 4 ? max(ulo, r0) : r0, vhi = type == 4 ? min(uhi, r1) : r1;
       const __half* W = type == 0 ? L.qkv_w : type == 1 ? L.o_w : type == 2 ? L.gateup_w : type == 3 ? L.down_w : p.head_w;
-      if (vlo < vhi) produce_matrix(W, g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, w, NB <= 2 && (type == 1 || type == 3));
+      if (vlo < vhi) produce_matrix(W, g.K, g.KP, g.KS, r0, r1, vlo, vhi, m, p.stages, s, ph, w, type == 1 || type == 3);
       if (type == 0 && s_ctl.valid) {
         // the K/V pages of this CTA's attention work item: cached rows do not depend on this step, so they queue right
         // behind the QKV weights and are in shared memory before q exists
@@ -1144,53 +1113,40 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
         const bool dense = seq == 0;
         stage_rms<NLD>(m.xs, xpitch_h, dense ? nullptr : p.x_ll, p.x, p.B, p.H, gm, p.eps, m.s_red, dense ? 0u : epx, w);
       }
-      if (!DENSE && !pro) {
-        // O / down projection, flag-in-data mode: k-outer, chunks multiplied as they arrive (consume_korder)
+      if (!pro) {
+        // O / down projection: k-outer, chunks multiplied as they arrive (consume_korder)
         stamp(p, l, 10 + type * 2);
-        consume_korder<NB>(m, type == 1 ? p.attn_ll : p.act_ll, (type == 1 ? p.qd : p.ffn) >> 1, g.K, g.KS, ntile, p.B, type == 1 ? epl + 3 : epl + 5,
-                           p.stages, rs, rph, w);
+        const int grid = ncta, nsplit = p.nsplit, ncomb = p.ncomb, kvh = p.kvh, items = p.B * p.kvh * p.nsplit, KSc = g.KS, gun = 2 * p.ffn;
+        if (type == 1) {
+          // chunk j of the attention output = kv heads [2j*KS/256 ...): produced by the combiner CTAs of those kv heads
+          consume_korder<NB, DENSE>(m, p.attn_ll, p.attnd, p.fa, [=](int c, int kcol) {
+            if (c >= items) return false;
+            const int split = c % nsplit, kv = (c / nsplit) % kvh;
+            const int e0 = kv * (DS_G * DS_HD);
+            return split < ncomb && e0 < kcol + KSc && e0 + DS_G * DS_HD > kcol;
+          }, ncta, g.K, g.KS, ntile, p.B, epl + 3, p.stages, rs, rph, w);
+        } else {
+          // chunk j of the SwiGLU activations <- gate/up rows [2*kcol, 2*(kcol+KS)): the CTAs that own those rows
+          consume_korder<NB, DENSE>(m, p.act_ll, p.actd, p.fact, [=](int c, int kcol) {
+            int a0, a1;
+            rows_of_cta(gun, 4, c, grid, a0, a1);
+            return a0 < 2 * (kcol + KSc) && a1 > 2 * kcol;
+          }, ncta, g.K, g.KS, ntile, p.B, epl + 5, p.stages, rs, rph, w);
+        }
         cons_sync();
         stamp(p, l, 24 + type);
-        epilogue_ll<NB, false>(m, r0, r1, 0, ntile, p.B, 1, p.x_ll, p.xd, p.H >> 1, type == 1 ? epl + 4 : epl + 6, s_res);
+        epilogue_ll<NB, DENSE>(m, r0, r1, 0, ntile, p.B, 1, p.x_ll, p.xd, p.H >> 1, type == 1 ? epl + 4 : epl + 6, s_res);
       }
       const int nkp = g.K / g.KP;
-      const int xs_buf = p.B * (g.KP + XS_PAD);          // halves per staging buffer of a k-phase
-      // dense mode: the next k-phase's activations are in flight (registers) while this one is consumed.  Batch 8: k-phases of
-      // 2048 columns, two staging buffers.  Batch 4: k-phases of 7168 columns (14 loads per thread), one buffer.
-      constexpr bool DBUF = NB >= 8;
-      constexpr int PF = DBUF ? NB : 14;
-      uint4 pre[PF];
-      if constexpr (DENSE) if (!pro) {
-        wait_flags(type == 1 ? p.fa : p.fact, type == 1 ? epl + 3 : epl + 5, ncta, all_ctas, w, 21);
-        const __half* src = type == 1 ? p.attnd : p.actd;
-        if (nkp == 1) {                                   // whole input in one batch (KP <= 4096: 2*NB loads per thread)
-          uint4 v[2 * NB];
-          dense_issue<2 * NB>(v, src, g.K, p.B, 0, g.KP);
-          dense_store<2 * NB>(v, m.xs, g.KP + XS_PAD, p.B, g.KP);
-        } else {                                          // k-phased
-          dense_issue<PF>(pre, src, g.K, p.B, 0, g.KP);
-          dense_store<PF>(pre, m.xs, g.KP + XS_PAD, p.B, g.KP);
-        }
-      }
-      for (int k0 = 0, kpi = 0; k0 < g.K && (DENSE || pro); k0 += g.KP, ++kpi) {
+      for (int k0 = 0; k0 < g.K && pro; k0 += g.KP) {          // (RMSNorm phases stage the whole hidden row: one k-phase)
         const __half* xcur = m.xs;
-        cons_sync();                                      // staged activations visible; every warp is done with the previous k-phase
-        if constexpr (DENSE) if (!pro) {
-          if (DBUF) xcur = m.xs + (kpi & 1) * xs_buf;
-          if (k0 + g.KP < g.K) dense_issue<PF>(pre, type == 1 ? p.attnd : p.actd, g.K, p.B, k0 + g.KP, g.KP);
-        }
+        cons_sync();                                      // staged activations visible
         if (k0 == 0) stamp(p, l, 10 + type * 2);
         const int gt = nkp > 1 ? ntile : p.group_tiles;
         for (int t0 = 0; t0 < ntile; t0 += gt) {
           const int t1 = min(ntile, t0 + gt);
           consume_tiles<NB>(m, xcur, g.KP, g.KS, t0, t1, tlo, thi, k0 > 0, p.B, p.stages, rs, rph, w);
-          if (k0 + g.KP < g.K) {                 // more k-phases to accumulate
-            if constexpr (DENSE) if (!pro) {
-              if (!DBUF) cons_sync();            // one buffer: every warp is done reading it
-              dense_store<PF>(pre, m.xs + (DBUF ? ((kpi + 1) & 1) * xs_buf : 0), g.KP + XS_PAD, p.B, g.KP);
-            }
-            continue;
-          }
+          if (k0 + g.KP < g.K) continue;         // more k-phases to accumulate
           cons_sync();
           if (t1 == ntile) stamp(p, l, 24 + type);
           if (type == 0) epilogue_ll<NB, DENSE>(m, r0, r1, t0, t1, p.B, 0, p.qkv_ll, p.qkvd, p.qkvw >> 1, epl + 1, s_res);
@@ -1264,14 +1220,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
 }  // namespace
 
 // host side ---------------------------------------------------------------------------------------------------
-static int ds_pick_kp(int K, int B, size_t cap_bytes) {
-  // prefer k-phases made of full 1024-column stages (32 KB in flight per ring slot)
-  for (int kp = 16384; kp >= 1024; kp -= 1024)
-    if (K % kp == 0 && kp <= K && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= cap_bytes) return kp;
-  for (int kp = 16384; kp >= 256; kp -= 256)
-    if (K % kp == 0 && kp <= K && static_cast<size_t>(B) * (kp + XS_PAD) * 2 <= cap_bytes) return kp;
-  return 0;
-}
 static int ds_pick_ks(int KP) {
   for (int ks = 1024; ks >= 256; ks -= 256)
     if (KP % ks == 0) return ks;
@@ -1309,27 +1257,15 @@ static int ds_plan(const DecodeStreamArgs& a, DsParams& p, size_t* smem_out) {
   TB_CHECK(a.heads == a.kvh * DS_G && a.qd == a.heads * DS_HD && a.page_size == DS_PAGE, "fused decode step is specialised for 128-dim heads, 4 q heads per kv head, 64-position pages");
   TB_CHECK(a.ffn % 4 == 0 && a.qkvw % 4 == 0 && a.head_rows % 2 == 0, "row counts must divide into exchange units");
   TB_CHECK(a.num_sms <= GV_CONS, "candidate merge handles <= 256 CTAs");
-  const size_t xcap = 72 * 1024;
-  const bool nbc8 = B > 4;
-  const bool dense = B > 2;            // batch bucket >= 4: dense exchange, k-phased down projection with double-buffered staging
+  // RMSNorm phases (QKV, gate/up, heads) stage the whole hidden row; the O / down projections take their input chunk by
+  // chunk into warp-private slices (consume_korder), so the staging buffer is sized by the hidden row alone
   const int Ks[5] = {a.H, a.qd, a.H, a.ffn, a.H};
-  int kpmax = 0;
   for (int i = 0; i < 5; ++i) {
-    int kp = ds_pick_kp(Ks[i], B, xcap);
-    if (nbc8 && i == 3 && kp > 2048) {            // batch 8: double-buffered k-phases of <= 2048 columns
-      kp = 0;
-      for (int c = 2048; c >= 256 && kp == 0; c -= (c > 1024 ? 1024 : 256))
-        if (Ks[i] % c == 0) kp = c;
-    }
-    if (dense && !nbc8 && i == 3) TB_CHECK(kp <= 7168, "batch-4 down projection prefetches k-phases of <= 7168 columns");
-    if (dense && i == 1) TB_CHECK(kp == Ks[i] && kp <= 4096, "dense O-projection staging handles K <= 4096 in one batch");
-    TB_CHECK(kp > 0, "decode GEMV K must be a multiple of 256");
-    if (i == 0 || i == 2 || i == 4) TB_CHECK(kp == Ks[i], "fused RMSNorm needs the whole hidden row staged");
-    p.kp[i] = kp;
-    p.ks[i] = ds_pick_ks(kp);
-    const int need = (nbc8 && i == 3 && kp < Ks[i]) ? 2 * (kp + XS_PAD) - XS_PAD : kp;     // batch 8: two staging buffers for the k-phased projection
-    if (need > kpmax) kpmax = need;
+    TB_CHECK(Ks[i] % 256 == 0, "decode GEMV K must be a multiple of 256");
+    p.kp[i] = Ks[i];
+    p.ks[i] = ds_pick_ks(Ks[i]);
   }
+  const int kpmax = a.H;
   const int nbc = B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8;
   const int Ns[5] = {a.qkvw, a.H, 2 * a.ffn, a.H, a.head_rows};
   const int units[5] = {2, 2, 4, 2, 2};
@@ -1338,12 +1274,11 @@ static int ds_plan(const DecodeStreamArgs& a, DsParams& p, size_t* smem_out) {
     const int rows = ((Ns[i] / units[i] + a.num_sms - 1) / a.num_sms) * units[i] + units[i] + (Ns[i] % units[i]);
     const int t = (rows + GV_TILE - 1) / GV_TILE;
     if (t > max_tiles) max_tiles = t;
-    if (Ks[i] / p.kp[i] > 1) TB_CHECK(t * GV_WARPS * GV_TILE * nbc * 4 <= 28 * 1024, "k-phased projection with too many row tiles per CTA");
-    if (i == 1 || i == 3) TB_CHECK(rows <= DS_RES_PITCH, "residual rows per CTA exceed the shared-memory residual buffer");
+    if (i == 1 || i == 3) TB_CHECK(rows <= DS_RES_PITCH && t <= 3, "O / down projection: at most 3 row tiles and 40 residual rows per CTA");
   }
-  // partial sums of a tile group: 28 KB, except at batch 8 where the region is sized by the attention scratch (20 KB) --
-  // that is what leaves room for a 4th ring stage next to the 66 KB of staged activations
-  int group_tiles = ((nbc == 8 ? 20 : 28) * 1024) / (GV_WARPS * GV_TILE * nbc * 4);
+  // partial sums of a tile group: 28 KB, except at batch 4..8 where the region is sized by the attention scratch (20 KB) --
+  // that is what leaves room for a 5th / 4th ring stage next to the 33 / 66 KB of staged activations
+  int group_tiles = ((nbc >= 4 ? 20 : 28) * 1024) / (GV_WARPS * GV_TILE * nbc * 4);
   if (group_tiles > max_tiles) group_tiles = max_tiles;
   int nsplit = a.num_sms / (B * a.kvh);
   if (nsplit < 1) nsplit = 1;
@@ -1360,7 +1295,7 @@ static int ds_plan(const DecodeStreamArgs& a, DsParams& p, size_t* smem_out) {
   const size_t fixed = ((static_cast<size_t>(B) * xs_cap * 2 + 127) & ~static_cast<size_t>(127)) + part_bytes + GV_MAXB * 4 * GV_WARPS * 4 +
                        2 * GV_MAXSTAGES * 8 + 256;
   const size_t stage = static_cast<size_t>(DS_STAGE_HALVES) * 2;
-  const size_t budget = 218 * 1024;   // + ~8 KB static shared memory (layer table, control blocks, finalize scratch) <= 227 KB
+  const size_t budget = 220 * 1024;   // + 6.3 KB static shared memory (layer table, control blocks, finalize scratch) <= 227 KB
   TB_CHECK(fixed + 2 * stage <= budget, "decode step shared memory budget exceeded");
   int st = static_cast<int>((budget - fixed) / stage);
   if (st > GV_MAXSTAGES) st = GV_MAXSTAGES;

@@ -6,7 +6,6 @@
 #include <map>
 #include <set>
 #include <string>
-#include <tuple>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, free when no tool is attached
@@ -76,12 +75,8 @@ struct trace_b200_ctx {
   // prefill workspaces
   __half *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_attn = nullptr, *p_act = nullptr;
   // decode workspaces + state
-  __half *d_x = nullptr, *d_qkv = nullptr, *d_attn = nullptr, *d_act = nullptr;
-  float *d_part_o = nullptr, *d_part_ml = nullptr, *d_cand_val = nullptr;
-  int32_t *d_counters = nullptr, *d_cand_idx = nullptr;
-  DecodeState st{};
+  __half* d_x = nullptr;          // [8, hidden] input embedding of the next decode step (prefill's last row, then finalize's embedding)
   // KV pool
-  std::vector<__half*> k_pool, v_pool;
   int32_t* d_block_table = nullptr;
   std::vector<int32_t> h_block_table;
   std::vector<int> free_pages;
@@ -90,8 +85,9 @@ struct trace_b200_ctx {
   std::vector<bool> slot_used;
   // streamed KV layout (decode_stream.cu): one pool per layer, [page][kv head][K|V][64][128], chunk-swizzled rows
   std::vector<__half*> kv_pool;
-  // decode graphs.  v2: keyed by batch only (max_new / eos / pad / sampling live in device memory); v1 bakes them in
-  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
+  // decode graphs, keyed by batch size: nothing that varies between calls (max_new / eos / pad / sampling / forced ids) is a
+  // kernel parameter -- it lives in device memory (sst.ctrl)
+  std::map<int, cudaGraphExec_t> graphs;
   // decode runs on an engine-owned stream (graph capture is illegal on the legacy default stream)
   cudaStream_t dstream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -99,14 +95,10 @@ struct trace_b200_ctx {
   int last_decode_steps = 0;
   // fused decode step (decode_mega.cu)
   void* d_layer_table = nullptr;
-  unsigned* d_gbar = nullptr;
   unsigned long long* d_dbg = nullptr;
-  bool fused_decode = true;
-  int tm_relay = 0, gate_mode = 1, pf_ahead = 0, max_inflight = 0, early_release = 1, max_stages = 4, relay_sites = 63;   // fused decode-step switches (kernels.h)
-  bool attn_tc = true;            // tcgen05 attention (attention_tc.cu); TRACE_B200_ATTN_TC=0 selects the mma.sync kernel
-  // fused decode step, v2 (decode_stream.cu)
+  int max_stages = 0;             // TRACE_B200_STAGES: cap on the ring stages of the decode step (0 = what fits)
+  // fused decode step (decode_stream.cu)
   int poll_sleep_ns = 0, watchdog_ms = 4000;
-  int decode_v = 2;               // TRACE_B200_DECODE=1 selects the round-1 kernel (decode_mega.cu) with its own KV layout
   int cooperative = 1;
   void* d_exchange = nullptr;
   size_t exchange_bytes = 0;
@@ -245,60 +237,31 @@ int allocate_all(trace_b200_ctx* ctx) {
   if (dalloc(ctx, &ctx->p_h, Mp * H) || dalloc(ctx, &ctx->p_y, Mp * H) || dalloc(ctx, &ctx->p_qkv, Mp * ctx->qkvw) ||
       dalloc(ctx, &ctx->p_attn, Mp * qd) || dalloc(ctx, &ctx->p_act, Mp * c.ffn))
     return 1;
-  if (dalloc(ctx, &ctx->d_x, static_cast<size_t>(kMaxB) * H) || dalloc(ctx, &ctx->d_qkv, static_cast<size_t>(kMaxB) * ctx->qkvw) ||
-      dalloc(ctx, &ctx->d_attn, kMaxB * qd) || dalloc(ctx, &ctx->d_act, static_cast<size_t>(kMaxB) * c.ffn) ||
-      dalloc(ctx, &ctx->d_part_o, static_cast<size_t>(kMaxB) * c.kv_heads * 64 * 512) ||
-      dalloc(ctx, &ctx->d_part_ml, static_cast<size_t>(kMaxB) * c.kv_heads * 64 * 8) ||
-      dalloc(ctx, &ctx->d_counters, static_cast<size_t>(kMaxB) * c.kv_heads, true) ||
-      dalloc(ctx, &ctx->d_cand_val, static_cast<size_t>(kMaxB) * 1024) ||
-      dalloc(ctx, &ctx->d_cand_idx, static_cast<size_t>(kMaxB) * 1024))
+  if (dalloc(ctx, &ctx->d_x, static_cast<size_t>(kMaxB) * H)) return 1;
+  if (dalloc(ctx, &ctx->sst.pos, kMaxB, true) || dalloc(ctx, &ctx->sst.heads, kMaxB, true) ||
+      dalloc(ctx, &ctx->sst.finished, kMaxB, true) || dalloc(ctx, &ctx->sst.step, 1, true) ||
+      dalloc(ctx, &ctx->sst.done_step, 1, true) || dalloc(ctx, &ctx->sst.out_ids, static_cast<size_t>(kMaxB) * c.max_ctx, true) ||
+      dalloc(ctx, &ctx->sst.slot_ids, kMaxB, true))
     return 1;
-  if (dalloc(ctx, &ctx->st.pos, kMaxB, true) || dalloc(ctx, &ctx->st.heads, kMaxB, true) ||
-      dalloc(ctx, &ctx->st.finished, kMaxB, true) || dalloc(ctx, &ctx->st.step, 1, true) ||
-      dalloc(ctx, &ctx->st.done_step, 1, true) || dalloc(ctx, &ctx->st.out_ids, static_cast<size_t>(kMaxB) * c.max_ctx, true) ||
-      dalloc(ctx, &ctx->st.slot_ids, kMaxB, true))
-    return 1;
-  if (dalloc(ctx, &ctx->d_gbar, 4, true)) return 1;
   if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 32 + static_cast<size_t>(ctx->num_sms) * 32, true)) return 1;
   {
-    const char* env = getenv("TRACE_B200_DECODE_PEROP");
-    ctx->fused_decode = !(env != nullptr && atoi(env) == 1);
     auto env_int = [](const char* name, int lo, int hi, int dflt) {
       const char* e = getenv(name);
       return (e != nullptr && atoi(e) >= lo && atoi(e) <= hi) ? atoi(e) : dflt;
     };
-    // measured on B200 (profiles/r01_decode_ab.md): the TMEM reservoir keeps HBM busy through the grid barriers, but the
-    // barrier words then queue behind the weight stream and every barrier gets 2-4 us longer -- net loss, so it is off
-    // by default; a ring of 4 stages is as fast as 3 and faster than 5 (the queue only adds latency once HBM is saturated)
-    ctx->tm_relay = env_int("TRACE_B200_TM_RELAY", 0, 2, 0);
-    ctx->gate_mode = env_int("TRACE_B200_GATE_MODE", 0, 2, ctx->tm_relay ? 2 : 1);
-    ctx->pf_ahead = env_int("TRACE_B200_PF_AHEAD", 0, 64, 0);
-    ctx->max_inflight = env_int("TRACE_B200_INFLIGHT", 0, 3, 0);
-    ctx->early_release = env_int("TRACE_B200_EARLY_REL", 0, 1, 1);
-    ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 4);
-    ctx->relay_sites = env_int("TRACE_B200_TM_SITES", 0, 63, 63);
-    const char* env2 = getenv("TRACE_B200_ATTN_TC");
-    ctx->attn_tc = (env2 != nullptr) ? atoi(env2) == 1 : true;   // tcgen05 attention: 2.0x (ViT) / 2.6x (prefill) the mma.sync kernel
-    ctx->decode_v = env_int("TRACE_B200_DECODE", 1, 2, 2);
     ctx->cooperative = env_int("TRACE_B200_COOP", 0, 1, 1);
-    if (ctx->decode_v == 2) ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
+    ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
     ctx->poll_sleep_ns = env_int("TRACE_B200_POLL_SLEEP", 0, 5000, 0);
     ctx->watchdog_ms = env_int("TRACE_B200_WATCHDOG_MS", 1, 3600000, 4000);    // compute-sanitizer runs need minutes
   }
   // ---- KV pool ----
   const size_t page_elems = static_cast<size_t>(c.kv_heads) * kPage * c.head_dim;
-  ctx->k_pool.resize(c.layers);
-  ctx->v_pool.resize(c.layers);
   ctx->kv_pool.resize(c.layers);
   for (int i = 0; i < c.layers; ++i) {
-    if (ctx->decode_v == 2) {
-      // zero-filled: a partially filled page is streamed whole and its unwritten rows meet probability 0 in P.V
-      if (dalloc(ctx, &ctx->kv_pool[i], 2 * page_elems * c.kv_pages, true)) return 1;
-    } else if (dalloc(ctx, &ctx->k_pool[i], page_elems * c.kv_pages) || dalloc(ctx, &ctx->v_pool[i], page_elems * c.kv_pages)) {
-      return 1;
-    }
+    // zero-filled: a partially filled page is streamed whole and its unwritten rows meet probability 0 in P.V
+    if (dalloc(ctx, &ctx->kv_pool[i], 2 * page_elems * c.kv_pages, true)) return 1;
   }
-  if (ctx->decode_v == 2) {
+  {
     size_t offs[16];
     ctx->exchange_bytes = decode_stream_exchange_bytes(c.hidden, ctx->qkvw, c.heads * c.head_dim, c.ffn, ctx->num_sms, offs);
     uint8_t* ex = nullptr;
@@ -313,8 +276,6 @@ int allocate_all(trace_b200_ctx* ctx) {
     TB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_err), 4, cudaHostAllocMapped));
     *ctx->h_err = 0;
     TB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_err), ctx->h_err, 0));
-    ctx->sst.pos = ctx->st.pos; ctx->sst.heads = ctx->st.heads; ctx->sst.finished = ctx->st.finished; ctx->sst.step = ctx->st.step;
-    ctx->sst.done_step = ctx->st.done_step; ctx->sst.out_ids = ctx->st.out_ids; ctx->sst.slot_ids = ctx->st.slot_ids;
     ctx->sst.ctrl = ctx->d_ctrl; ctx->sst.forced = ctx->d_forced;
   }
   if (dalloc(ctx, &ctx->d_block_table, static_cast<size_t>(kMaxSlots) * ctx->max_pages_seq, true)) return 1;
@@ -449,14 +410,8 @@ int vit_chunk(trace_b200_ctx* ctx, const __half* pixels, int F, __half* res_out,
   for (const VitLayer& l : ctx->vit) {
     RUN(layernorm_f16(ctx->v_h, D, l.ln1_w, l.ln1_b, c.vit_ln_eps, ctx->v_y, D, M, D, s));
     RUN(gemm_f16(ctx->v_y, D, l.qkv_w, D, ctx->v_qkv, 3 * D, M, 3 * D, D, l.qkv_b, nullptr, 0, 0, 0, sms, s));
-    if (ctx->attn_tc) {
-      RUN(attention_tc_fwd(ctx->v_qkv, 3 * D, ctx->v_attn, NT, D, static_cast<int64_t>(NT) * D, 0, D, 2 * D, c.vit_heads, 1, F, hdv, 0,
-                           1.0f / sqrtf(static_cast<float>(hdv)), s));
-    } else {
-      RUN(attention_fwd(ctx->v_qkv, ctx->v_qkv + D, ctx->v_qkv + 2 * D, ctx->v_attn, NT, 3 * D, 3 * D, D,
-                        static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * 3 * D, static_cast<int64_t>(NT) * D,
-                        c.vit_heads, 1, F, hdv, 0, 1.0f / sqrtf(static_cast<float>(hdv)), s));
-    }
+    RUN(attention_tc_fwd(ctx->v_qkv, 3 * D, ctx->v_attn, NT, D, static_cast<int64_t>(NT) * D, 0, D, 2 * D, c.vit_heads, 1, F, hdv, 0,
+                         1.0f / sqrtf(static_cast<float>(hdv)), s));
     RUN(gemm_f16(ctx->v_attn, D, l.out_w, D, ctx->v_h, D, M, D, D, l.out_b, ctx->v_h, D, 0, 0, sms, s));
     RUN(layernorm_f16(ctx->v_h, D, l.ln2_w, l.ln2_b, c.vit_ln_eps, ctx->v_y, D, M, D, s));
     RUN(gemm_f16(ctx->v_y, D, l.fc1_w, D, ctx->v_mlp, c.vit_mlp, M, c.vit_mlp, D, l.fc1_b, nullptr, 0, 1, 0, sms, s));
@@ -480,64 +435,14 @@ int decoder_layers_prefill(trace_b200_ctx* ctx, int B, int S, const int32_t* slo
     RUN(rmsnorm_f16(ctx->p_h, H, l.ln1, c.rms_eps, ctx->p_y, H, M, H, s));
     RUN(gemm_f16(ctx->p_y, H, l.qkv_w, H, ctx->p_qkv, ctx->qkvw, M, ctx->qkvw, H, nullptr, nullptr, 0, 0, 0, sms, s));
     RUN(rope_kv_prefill(ctx->p_qkv, B, S, c.heads, c.kv_heads, c.head_dim, ctx->rope_cos, ctx->rope_sin,
-                        ctx->decode_v == 2 ? ctx->kv_pool[i] : ctx->k_pool[i], ctx->decode_v == 2 ? nullptr : ctx->v_pool[i],
-                        ctx->d_block_table, slot_ids_dev, ctx->max_pages_seq, kPage, s));
-    if (ctx->attn_tc) {
-      RUN(attention_tc_fwd(ctx->p_qkv, ctx->qkvw, ctx->p_attn, S, qd, static_cast<int64_t>(S) * qd, 0, qd, qd + kvd, c.heads,
-                           c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
-    } else {
-      RUN(attention_fwd(ctx->p_qkv, ctx->p_qkv + qd, ctx->p_qkv + qd + kvd, ctx->p_attn, S, ctx->qkvw, ctx->qkvw, qd,
-                        static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * ctx->qkvw, static_cast<int64_t>(S) * qd,
-                        c.heads, c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
-    }
+                        ctx->kv_pool[i], ctx->d_block_table, slot_ids_dev, ctx->max_pages_seq, kPage, s));
+    RUN(attention_tc_fwd(ctx->p_qkv, ctx->qkvw, ctx->p_attn, S, qd, static_cast<int64_t>(S) * qd, 0, qd, qd + kvd, c.heads,
+                         c.heads / c.kv_heads, B, c.head_dim, 1, 1.0f / sqrtf(static_cast<float>(c.head_dim)), s));
     RUN(gemm_f16(ctx->p_attn, qd, l.o_w, qd, ctx->p_h, H, M, H, qd, nullptr, ctx->p_h, H, 0, 0, sms, s));
     RUN(rmsnorm_f16(ctx->p_h, H, l.ln2, c.rms_eps, ctx->p_y, H, M, H, s));
     RUN(gemm_f16(ctx->p_y, H, l.gateup_w, H, ctx->p_act, c.ffn, M, 2 * c.ffn, H, nullptr, nullptr, 0, 0, 1, sms, s));
     RUN(gemm_f16(ctx->p_act, c.ffn, l.down_w, c.ffn, ctx->p_h, H, M, H, c.ffn, nullptr, ctx->p_h, H, 0, 0, sms, s));
   }
-  return 0;
-}
-
-int decode_nsplit(const trace_b200_ctx* ctx, int B) {
-  int n = (2 * ctx->num_sms) / (ctx->c.kv_heads * B);
-  if (n < 1) n = 1;
-  if (n > 32) n = 32;
-  return n;
-}
-
-// one decode step: 32 x {qkv gemv, attention, o gemv, gate/up gemv, down gemv} + head + finalize
-int decode_step(trace_b200_ctx* ctx, int B, int eos, int pad, float* logits_out, cudaStream_t s) {
-  const trace_b200_config& c = ctx->c;
-  const int H = c.hidden, qd = c.heads * c.head_dim;
-  if (ctx->fused_decode) {
-    DecodeMegaArgs a{};
-    a.B = B; a.H = H; a.qkvw = ctx->qkvw; a.qd = qd; a.ffn = c.ffn; a.layers = c.layers; a.heads = c.heads; a.kvh = c.kv_heads;
-    a.vocab = c.vocab; a.head_rows = ctx->head_rows; a.n_valid = ctx->total_vocab; a.max_ctx = c.max_ctx; a.num_sms = ctx->num_sms;
-    a.eps = c.rms_eps; a.layer_table_dev = ctx->d_layer_table; a.final_norm = ctx->final_norm; a.head_w = ctx->head_w;
-    a.x = ctx->d_x; a.qkv = ctx->d_qkv; a.attn = ctx->d_attn; a.act = ctx->d_act; a.cos_tab = ctx->rope_cos; a.sin_tab = ctx->rope_sin;
-    a.block_table = ctx->d_block_table; a.max_pages = ctx->max_pages_seq; a.page_size = kPage; a.part_o = ctx->d_part_o;
-    a.part_ml = ctx->d_part_ml; a.counters = ctx->d_counters; a.cand_val = ctx->d_cand_val; a.cand_idx = ctx->d_cand_idx;
-    a.logits_out = logits_out; a.embed = ctx->embed; a.time_tab = ctx->time_tab; a.score_tab = ctx->score_tab; a.sync_tab = ctx->sync_tab;
-    a.eos = eos; a.pad = pad; a.st = ctx->st; a.gbar = ctx->d_gbar; a.dbg = ctx->d_dbg;
-    a.tm_relay = ctx->tm_relay; a.gate_mode = ctx->gate_mode; a.pf_ahead = ctx->pf_ahead; a.max_inflight = ctx->max_inflight; a.early_release = ctx->early_release; a.max_stages = ctx->max_stages; a.relay_sites = ctx->relay_sites;
-    RUN(decode_step_fused(a, s));
-    return 0;
-  }
-  const int nsplit = decode_nsplit(ctx, B);
-  for (int i = 0; i < c.layers; ++i) {
-    const LlmLayer& l = ctx->llm[i];
-    RUN(gemv_f16(l.qkv_w, ctx->d_x, H, ctx->d_qkv, ctx->qkvw, B, ctx->qkvw, H, 1, l.ln1, c.rms_eps, 0, s));
-    RUN(attn_decode(ctx->d_qkv, B, c.heads, c.kv_heads, c.head_dim, ctx->rope_cos, ctx->rope_sin, ctx->k_pool[i], ctx->v_pool[i],
-                    ctx->d_block_table, ctx->max_pages_seq, kPage, ctx->st, nsplit, c.max_ctx, ctx->d_part_o, ctx->d_part_ml,
-                    ctx->d_counters, ctx->d_attn, s));
-    RUN(gemv_f16(l.o_w, ctx->d_attn, qd, ctx->d_x, H, B, H, qd, 0, nullptr, 0.f, 1, s));
-    RUN(gemv_f16(l.gateup_w, ctx->d_x, H, ctx->d_act, c.ffn, B, 2 * c.ffn, H, 1, l.ln2, c.rms_eps, 2, s));
-    RUN(gemv_f16(l.down_w, ctx->d_act, c.ffn, ctx->d_x, H, B, H, c.ffn, 0, nullptr, 0.f, 1, s));
-  }
-  RUN(head_gemv(ctx->head_w, ctx->d_x, H, B, ctx->total_vocab, ctx->head_rows, H, ctx->final_norm, c.rms_eps, c.vocab, ctx->st,
-                ctx->d_cand_val, ctx->d_cand_idx, logits_out, s));
-  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, head_gemv_ncand(), B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
-                      ctx->score_tab, ctx->sync_tab, H, ctx->st, ctx->d_x, 1, s));
   return 0;
 }
 
@@ -555,14 +460,14 @@ DecodeStreamArgs stream_args(trace_b200_ctx* ctx, int B, int layers_run, float* 
   return a;
 }
 
-// one launch of the streamed decode step (decode_stream.cu).  layers_run = 0: heads only, on the prefill's last hidden state
-int decode_step_v2(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, cudaStream_t s) {
+// one launch of the fused decode step (decode_stream.cu).  layers_run = 0: heads only, on the prefill's last hidden state
+int decode_step(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, cudaStream_t s) {
   const DecodeStreamArgs a = stream_args(ctx, B, layers_run, logits_out);
   RUN(decode_stream_step(a, s));
   return 0;
 }
 
-int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new, int eos, int pad,
+int decode_loop(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new, int eos, int pad,
               int64_t* ids_out_host, int* n_out, float* logits_out_dev, cudaStream_t s) {
   const trace_b200_config& c = ctx->c;
   std::vector<int32_t> pos(B), zeros(kMaxB, 0);
@@ -585,12 +490,12 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
     ctx->launches_since_reset = 0;
   }
   TB_CUDA(cudaMemcpyAsync(ctx->d_ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.heads, heads_inout_host, B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.finished, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.heads, heads_inout_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.finished, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaStreamSynchronize(s));     // ctrl / pos / forced_host are host stack or heap memory
   ctx->forced_host.clear();
   const size_t lstride = static_cast<size_t>(B) * ctx->total_vocab;
@@ -602,14 +507,14 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
   };
   int done = 0;
   auto poll_done = [&]() -> int {
-    cudaError_t e = cudaMemcpyAsync(&done, ctx->st.done_step, 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaMemcpyAsync(&done, ctx->sst.done_step, 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(e, "decode step");
     return 0;
   };
   TB_CUDA(cudaEventRecord(ctx->ev_t0, s));
   // token 0: heads on the prefill's last hidden state, no decoder pass, positions do not advance
-  if (decode_step_v2(ctx, B, 0, logits_out_dev, s)) return 1;
+  if (decode_step(ctx, B, 0, logits_out_dev, s)) return 1;
   ++ctx->launches_since_reset;
   int steps_run = 1;
   if (logits_out_dev != nullptr || max_new <= 2) {
@@ -617,31 +522,30 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
     for (; steps_run < max_new; ++steps_run) {
       if (poll_done()) return 1;
       if (done) break;
-      if (decode_step_v2(ctx, B, c.layers, logits_out_dev ? logits_out_dev + lstride * steps_run : nullptr, s)) return 1;
+      if (decode_step(ctx, B, c.layers, logits_out_dev ? logits_out_dev + lstride * steps_run : nullptr, s)) return 1;
       ++ctx->launches_since_reset;
     }
   } else {
     // production path: step 1 eager (also sets kernel attributes), then one captured step replayed.  Nothing that varies
     // between calls (max_new, eos, pad, sampling, forced ids) is a kernel parameter, so the graph is keyed by batch only.
-    if (decode_step_v2(ctx, B, c.layers, nullptr, s)) return 1;
+    if (decode_step(ctx, B, c.layers, nullptr, s)) return 1;
     ++steps_run;
     cudaGraphExec_t exec = nullptr;
-    const auto gkey = std::make_tuple(B, 0, 0, 0);
-    auto it = ctx->graphs.find(gkey);
+    auto it = ctx->graphs.find(B);
     if (it != ctx->graphs.end()) {
       exec = it->second;
     } else {
       cudaGraph_t graph = nullptr;
       TB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const int64_t before = ctx->launches;
-      const int rc = decode_step_v2(ctx, B, c.layers, nullptr, s);
+      const int rc = decode_step(ctx, B, c.layers, nullptr, s);
       ctx->launches = before;
       cudaError_t ce = cudaStreamEndCapture(s, &graph);
       TB_CHECK(rc == 0, std::string("decode step failed during graph capture: ") + tb::get_error());
       TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("graph capture failed: ") + cudaGetErrorString(ce));
       TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      ctx->graphs[gkey] = exec;
+      ctx->graphs[B] = exec;
     }
     while (steps_run < max_new) {
       const int burst = (max_new - steps_run < 16) ? (max_new - steps_run) : 16;
@@ -660,8 +564,8 @@ int decode_v2(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* he
   ctx->last_decode_steps = steps_run;
   const int n = done ? done : (steps_run < max_new ? steps_run : max_new);
   std::vector<int64_t> tmp(static_cast<size_t>(B) * max_new);
-  TB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->st.out_ids, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
-  TB_CUDA(cudaMemcpyAsync(heads_inout_host, ctx->st.heads, B * 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->sst.out_ids, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaMemcpyAsync(heads_inout_host, ctx->sst.heads, B * 4, cudaMemcpyDeviceToHost, s));
   TB_CUDA(cudaStreamSynchronize(s));
   for (int b = 0; b < B; ++b) {
     memcpy(ids_out_host + static_cast<size_t>(b) * max_new, tmp.data() + static_cast<size_t>(b) * max_new, static_cast<size_t>(n) * 8);
@@ -737,15 +641,13 @@ int trace_b200_finalize_weights(trace_b200_ctx* ctx) {
   TB_CHECK(ctx != nullptr, "null context");
   for (const std::string& n : ctx->expected) TB_CHECK(ctx->loaded.count(n) == 1, "missing weight " + n);
   {
-    TB_CHECK(decode_mega_layer_table_bytes() == 8 * static_cast<int>(sizeof(void*)) && decode_stream_layer_bytes() == 8 * static_cast<int>(sizeof(void*)),
-             "layer table layout mismatch");
+    TB_CHECK(decode_stream_layer_bytes() == 8 * static_cast<int>(sizeof(void*)), "layer table layout mismatch");
     std::vector<const void*> tab;
     for (int i = 0; i < ctx->c.layers; ++i) {
       const LlmLayer& l = ctx->llm[i];
-      const void* p6 = ctx->decode_v == 2 ? static_cast<const void*>(ctx->kv_pool[i]) : static_cast<const void*>(ctx->k_pool[i]);
-      const void* p7 = ctx->decode_v == 2 ? nullptr : static_cast<const void*>(ctx->v_pool[i]);
       for (const void* q : {static_cast<const void*>(l.ln1), static_cast<const void*>(l.qkv_w), static_cast<const void*>(l.o_w),
-                            static_cast<const void*>(l.ln2), static_cast<const void*>(l.gateup_w), static_cast<const void*>(l.down_w), p6, p7})
+                            static_cast<const void*>(l.ln2), static_cast<const void*>(l.gateup_w), static_cast<const void*>(l.down_w),
+                            static_cast<const void*>(ctx->kv_pool[i]), static_cast<const void*>(nullptr)})
         tab.push_back(q);
     }
     if (ctx->d_layer_table == nullptr) {
@@ -840,9 +742,9 @@ int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, co
     TB_CHECK(static_cast<int>(ctx->slot_pages[sl].size()) * kPage >= S, "slot too small for the prompt");
     ctx->slot_len[sl] = S;
   }
-  TB_CUDA(cudaMemcpyAsync(ctx->st.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->p_h, embeds, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
-  if (decoder_layers_prefill(ctx, B, S, ctx->st.slot_ids, s)) return 1;
+  if (decoder_layers_prefill(ctx, B, S, ctx->sst.slot_ids, s)) return 1;
   if (hidden_out != nullptr)
     TB_CUDA(cudaMemcpyAsync(hidden_out, ctx->p_h, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
   // last position of every row -> decode activation buffer
@@ -862,94 +764,15 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   TB_CUDA(cudaEventRecord(ctx->ev_in, static_cast<cudaStream_t>(stream)));
   cudaStream_t s = ctx->dstream;
   TB_CUDA(cudaStreamWaitEvent(s, ctx->ev_in, 0));
-  std::vector<int32_t> pos(B), zeros(kMaxB, 0);
   for (int b = 0; b < B; ++b) {
     const int sl = slots_host[b];
     TB_CHECK(sl >= 0 && sl < kMaxSlots && ctx->slot_used[sl] && ctx->slot_len[sl] > 0, "decode on a slot without prefill");
     TB_CHECK(ctx->slot_len[sl] + max_new - 1 <= static_cast<int>(ctx->slot_pages[sl].size()) * kPage, "slot too small for max_new tokens");
     TB_CHECK(ctx->slot_len[sl] + max_new - 1 <= c.max_ctx, "sequence exceeds max_ctx");
     TB_CHECK(heads_inout_host[b] >= -1 && heads_inout_host[b] <= 2, "head id must be -1, 0, 1 or 2");
-    pos[b] = ctx->slot_len[sl];
   }
   TB_CHECK(max_new <= c.max_ctx, "max_new exceeds the output buffer");
-  if (ctx->decode_v == 2) return decode_v2(ctx, slots_host, B, heads_inout_host, max_new, eos, pad, ids_out_host, n_out, logits_out_dev, s);
-  TB_CHECK(ctx->do_sample == 0 && ctx->forced_host.empty(), "sampling / forced ids need the streamed decode step (TRACE_B200_DECODE=2)");
-  ctx->st.max_new = max_new;
-  TB_CUDA(cudaMemcpyAsync(ctx->st.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.heads, heads_inout_host, B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.finished, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
-  TB_CUDA(cudaMemcpyAsync(ctx->st.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
-  const size_t lstride = static_cast<size_t>(B) * ctx->total_vocab;
-
-  TB_CUDA(cudaEventRecord(ctx->ev_t0, s));
-  // token 0: heads on the prefill's last hidden state, no decoder pass, positions do not advance
-  RUN(head_gemv(ctx->head_w, ctx->d_x, c.hidden, B, ctx->total_vocab, ctx->head_rows, c.hidden, ctx->final_norm, c.rms_eps, c.vocab,
-                ctx->st, ctx->d_cand_val, ctx->d_cand_idx, logits_out_dev, s));
-  RUN(decode_finalize(ctx->d_cand_val, ctx->d_cand_idx, head_gemv_ncand(), B, c.vocab, eos, pad, ctx->embed, ctx->time_tab,
-                      ctx->score_tab, ctx->sync_tab, c.hidden, ctx->st, ctx->d_x, 0, s));
-  int done = 0;
-  int steps_run = 1;
-  const int64_t per_step = ctx->fused_decode ? 1 : static_cast<int64_t>(c.layers) * 5 + 2;
-  auto poll_done = [&]() -> int {
-    TB_CUDA(cudaMemcpyAsync(&done, ctx->st.done_step, 4, cudaMemcpyDeviceToHost, s));
-    TB_CUDA(cudaStreamSynchronize(s));
-    return 0;
-  };
-  if (logits_out_dev != nullptr || max_new <= 2) {
-    // instrumented path: one eager step per token (parity tests read every step's logits)
-    for (; steps_run < max_new; ++steps_run) {
-      if (poll_done()) return 1;
-      if (done) break;
-      if (decode_step(ctx, B, eos, pad, logits_out_dev ? logits_out_dev + lstride * steps_run : nullptr, s)) return 1;
-    }
-  } else {
-    // production path: step 1 eager (also sets kernel attributes), then one captured step replayed
-    if (decode_step(ctx, B, eos, pad, nullptr, s)) return 1;
-    ++steps_run;
-    cudaGraphExec_t exec = nullptr;
-    const auto gkey = std::make_tuple(B, max_new, eos, pad);   // the captured v1 nodes bake these in as kernel parameters
-    auto it = ctx->graphs.find(gkey);
-    if (it != ctx->graphs.end()) {
-      exec = it->second;
-    } else {
-      cudaGraph_t graph = nullptr;
-      TB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int64_t before = ctx->launches;
-      const int rc = decode_step(ctx, B, eos, pad, nullptr, s);
-      ctx->launches = before;
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      TB_CHECK(rc == 0, std::string("decode step failed during graph capture: ") + tb::get_error());
-      TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-      TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-      cudaGraphDestroy(graph);
-      ctx->graphs[gkey] = exec;
-    }
-    while (steps_run < max_new) {
-      const int burst = (max_new - steps_run < 16) ? (max_new - steps_run) : 16;
-      for (int i = 0; i < burst; ++i) TB_CUDA(cudaGraphLaunch(exec, s));
-      steps_run += burst;
-      ctx->launches += per_step * burst;
-      if (poll_done()) return 1;
-      if (done) break;
-    }
-  }
-  TB_CUDA(cudaEventRecord(ctx->ev_t1, s));
-  if (poll_done()) return 1;
-  TB_CUDA(cudaEventElapsedTime(&ctx->last_decode_ms, ctx->ev_t0, ctx->ev_t1));
-  ctx->last_decode_steps = steps_run;
-  const int n = done ? done : (steps_run < max_new ? steps_run : max_new);
-  std::vector<int64_t> tmp(static_cast<size_t>(B) * max_new);
-  TB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->st.out_ids, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
-  TB_CUDA(cudaMemcpyAsync(heads_inout_host, ctx->st.heads, B * 4, cudaMemcpyDeviceToHost, s));
-  TB_CUDA(cudaStreamSynchronize(s));
-  for (int b = 0; b < B; ++b) {
-    memcpy(ids_out_host + static_cast<size_t>(b) * max_new, tmp.data() + static_cast<size_t>(b) * max_new, static_cast<size_t>(n) * 8);
-    ctx->slot_len[slots_host[b]] += n - 1;
-  }
-  *n_out = n;
-  return 0;
+  return decode_loop(ctx, slots_host, B, heads_inout_host, max_new, eos, pad, ids_out_host, n_out, logits_out_dev, s);
 }
 
 int trace_b200_set_sampling(trace_b200_ctx* ctx, int do_sample, float temperature, int top_k, uint64_t seed) {
@@ -975,7 +798,6 @@ int trace_b200_set_forced_ids(trace_b200_ctx* ctx, const int64_t* ids_host, int 
 
 int trace_b200_decode_plan(trace_b200_ctx* ctx, int B, int context_len, int32_t* out8) {
   TB_CHECK(ctx != nullptr && out8 != nullptr, "null argument");
-  TB_CHECK(ctx->decode_v == 2, "decode plan introspection needs the streamed decode step (TRACE_B200_DECODE=2)");
   return decode_stream_plan(stream_args(ctx, B, ctx->c.layers, nullptr), context_len, out8);
 }
 
@@ -1032,24 +854,10 @@ int trace_b200_op_rmsnorm(const void* x, const void* w, float eps, void* out, in
   return rmsnorm_f16(static_cast<const __half*>(x), D, static_cast<const __half*>(w), eps, static_cast<__half*>(out), D, rows, D,
                      static_cast<cudaStream_t>(stream));
 }
-int trace_b200_op_attention(const void* q, const void* k, const void* v, void* o, int seqlen, int q_stride, int kv_stride,
-                            int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride, int heads, int group, int batch,
-                            int head_dim, int causal, float scale, void* stream) {
-  return attention_fwd(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
-                       static_cast<__half*>(o), seqlen, q_stride, kv_stride, o_stride, q_bstride, kv_bstride, o_bstride, heads, group,
-                       batch, head_dim, causal, scale, static_cast<cudaStream_t>(stream));
-}
 int trace_b200_op_attention_tc(const void* qkv, int width, void* o, int seqlen, int heads, int kv_heads, int head_dim, int causal, int batch,
                                float scale, void* stream) {
   const int qd = heads * head_dim, kvd = kv_heads * head_dim;
   return attention_tc_fwd(static_cast<const __half*>(qkv), width, static_cast<__half*>(o), seqlen, qd, static_cast<int64_t>(seqlen) * qd, 0, qd,
                           qd + kvd, heads, heads / kv_heads, batch, head_dim, causal, scale, static_cast<cudaStream_t>(stream));
 }
-int trace_b200_op_gemv(const void* W, const void* x, void* out, int B, int N, int K, int pro, const void* gamma, float eps, int epi,
-                       void* stream) {
-  const int ldo = (epi == 2) ? N / 2 : N;
-  return gemv_f16(static_cast<const __half*>(W), static_cast<const __half*>(x), K, static_cast<__half*>(out), ldo, B, N, K, pro,
-                  static_cast<const __half*>(gamma), eps, epi, static_cast<cudaStream_t>(stream));
-}
-
 }  // extern "C"

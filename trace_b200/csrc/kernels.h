@@ -26,14 +26,7 @@ int vit_im2col(const __half* pixels, __half* out, int F, int image, int ps, int 
 int vit_embed_ln(const __half* patch, const __half* cls, const __half* pos, const __half* ln_w, const __half* ln_b,
                  float eps, __half* out, int F, int P, int D, cudaStream_t stream);
 
-// ---- attention.cu : flash-style attention on mma.sync (legacy tensor path, TRACE_B200_ATTN_TC=0; the default is attention_tc.cu) ----
-// Q/K/V element pointers with row strides (elements) and per-batch strides; head h uses columns [h*HD, (h+1)*HD)
-// of Q/O and [(h/group)*HD, ...) of K/V.  HD in {64, 128}.
-int attention_fwd(const __half* Q, const __half* K, const __half* V, __half* O, int seqlen, int q_stride,
-                  int kv_stride, int o_stride, int64_t q_bstride, int64_t kv_bstride, int64_t o_bstride, int heads,
-                  int group, int batch, int head_dim, int causal, float scale, cudaStream_t stream);
-
-// ---- attention_tc.cu : the same contraction on tcgen05 (TMA-fed, S / PV accumulators in TMEM) ------------------
+// ---- attention_tc.cu : softmax(Q K^T * scale [+ causal mask]) V on tcgen05 (TMA-fed, S / PV accumulators in TMEM) ----
 // qkv: fused activation [batch*seqlen, width]; Q/K/V heads at column offsets q_col0/k_col0/v_col0 (head h -> + h*HD).
 int attention_tc_fwd(const __half* qkv, int width, __half* O, int seqlen, int o_stride, int64_t o_bstride, int q_col0, int k_col0,
                      int v_col0, int heads, int group, int batch, int head_dim, int causal, float scale, cudaStream_t stream);
@@ -53,7 +46,7 @@ int splice_prefill(const int64_t* ids /*[B,L]*/, int B, int L, int T, const __ha
 
 // ---- rope_kv.cu : prefill RoPE (in place on the fused qkv buffer) + paged KV write ---------------------------
 int rope_kv_prefill(__half* qkv /*[B*S, (heads+2*kvh)*hd]*/, int B, int S, int heads, int kvh, int hd,
-                    const float* cos_tab, const float* sin_tab /*[max_pos, hd/2]*/, __half* k_pool, __half* v_pool,
+                    const float* cos_tab, const float* sin_tab /*[max_pos, hd/2]*/, __half* kv_pool,
                     const int32_t* block_table /*[slots,max_pages]*/, const int32_t* slot_ids /*[B]*/, int max_pages,
                     int page_size, cudaStream_t stream);
 
@@ -72,72 +65,6 @@ __host__ __device__ inline int64_t kv_tile_offset(int page, int kvh, int kv, int
 }
 // column of element d of the row at in-page position pos: 16-byte chunks (8 halves) are XOR-swizzled with pos & 7
 __host__ __device__ inline int kv_chunk_swz(int d, int pos) { return (((d >> 3) ^ (pos & 7)) << 3) | (d & 7); }
-
-// ---- decode.cu -------------------------------------------------------------------------------------------
-struct DecodeState {           // device-resident generation state (no host round trips inside the loop)
-  int32_t* pos;                // [B] number of cached positions (== position id of the token being fed)
-  int32_t* heads;              // [B] active head 0 text / 1 time / 2 score ; -1 = text-only (no heads given)
-  int32_t* finished;           // [B]
-  int32_t* step;               // [1] tokens emitted so far
-  int32_t* done_step;          // [1] step count at which all rows were finished (0 = not yet)
-  int64_t* out_ids;            // [B, max_new]
-  int32_t* slot_ids;           // [B]
-  int max_new;
-};
-
-// out[b, n] = epi( W[n,:] · pro(x[b,:]) ), B <= 8, N % 16 == 0, K % 256 == 0.
-// pro: 0 none, 1 RMSNorm(gamma, eps).  epi: 0 store, 1 residual add in place, 2 SwiGLU pairs (out has N/2 cols).
-int gemv_f16(const __half* W, const __half* x, int ldx, __half* out, int ldo, int B, int N, int K, int pro,
-             const __half* gamma, float eps, int epi, cudaStream_t stream);
-
-// fused: RoPE(q,k) + KV append + split-KV attention + last-CTA combine -> attn_out [B, heads*hd]
-int attn_decode(const __half* qkv, int B, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
-                __half* k_pool, __half* v_pool, const int32_t* block_table, int max_pages, int page_size,
-                const DecodeState& st, int nsplit, int max_ctx, float* part_o, float* part_ml, int32_t* counters,
-                __half* attn_out, cudaStream_t stream);
-
-// final RMSNorm + active-head GEMV + masked argmax candidates.  Wh: packed [Npad, K] rows = global token ids.
-int head_gemv(const __half* Wh, const __half* x, int ldx, int B, int n_valid, int Npad, int K, const __half* gamma,
-              float eps, int vocab, const DecodeState& st, float* cand_val, int32_t* cand_idx,
-              float* logits_out /*[B, n_valid] or null*/, cudaStream_t stream);
-
-int head_gemv_ncand();   // candidates per batch row written by head_gemv (= its grid size)
-
-// argmax over candidates, EOS/pad bookkeeping, head switch, next-token embedding dispatch, pos++.
-int decode_finalize(const float* cand_val, const int32_t* cand_idx, int ncand, int B, int vocab, int eos, int pad,
-                    const __half* embed, const __half* time_tab, const __half* score_tab, const __half* sync_tab,
-                    int H, const DecodeState& st, __half* x_next, int advance_pos, cudaStream_t stream);
-
-// ---- decode_mega.cu : the whole decode step as one persistent kernel -------------------------------------------
-struct DecodeMegaArgs {
-  int B, H, qkvw, qd, ffn, layers, heads, kvh, vocab, head_rows, n_valid, max_ctx, num_sms;
-  float eps;
-  const void* layer_table_dev;   // [layers] x {ln1, qkv_w, o_w, ln2, gateup_w, down_w, k_pool, v_pool} device pointers
-  const __half *final_norm, *head_w;
-  __half *x, *qkv, *attn, *act;
-  const float *cos_tab, *sin_tab;
-  const int32_t* block_table;
-  int max_pages, page_size;
-  float *part_o, *part_ml;
-  int32_t* counters;
-  float* cand_val;
-  int32_t* cand_idx;
-  float* logits_out;
-  const __half *embed, *time_tab, *score_tab, *sync_tab;
-  int eos, pad;
-  DecodeState st;
-  unsigned* gbar;                // [2] zero-initialised: grid barrier + exit counters
-  unsigned long long* dbg;       // optional timeline buffer [2][layers][10] (nullptr = off)
-  // tuning switches (engine.cu reads them from the environment when the context is created)
-  int tm_relay;                  // TMEM weight reservoir: 0 off, 1 on (default), 2 test mode (park greedily at every barrier)
-  int gate_mode;                 // producer waits for the attention K/V requests before 1: the O weights, 2: the gate/up weights, 0: never
-  int pf_ahead;                  // experimental TMA L2 prefetch distance of the weight stream in stages (0 = off, the default)
-  int max_inflight;              // weight-stream request throttle in stages (0 = ring depth)
-  int relay_sites;               // TMEM reservoir: which barriers park stages (bit = phase type that follows, bit 5 = before attention)
-  int early_release, max_stages; // ring stage handed back before its MMA chain (default 1); cap on ring stages (0 = what fits)
-};
-int decode_step_fused(const DecodeMegaArgs& a, cudaStream_t stream);
-int decode_mega_layer_table_bytes();
 
 // ---- decode_stream.cu : the decode step as one cooperative kernel, one HBM stream (weights + K/V pages), flag-in-data exchanges ----
 struct DecodeStreamState {     // device-resident generation state; nothing in it is baked into a captured graph

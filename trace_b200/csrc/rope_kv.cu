@@ -2,11 +2,10 @@
 // Operates in place on the fused qkv activation [B*S, (heads + 2*kvh) * hd] produced by the QKV GEMM:
 // q and k columns are rotated (rotate_half pairs d, d+hd/2; cos/sin tables hold the fp16-rounded values the
 // reference casts to, [max_pos, hd/2]); rotated k and raw v rows are appended to the page pool
-//   legacy layout (v_pool != nullptr): two pools [page][kv_head][page_size][hd] fp16, page = block_table[slot][pos / page_size].
-//   streamed layout (v_pool == nullptr, the default): ONE pool [page][kv_head][K|V][page_size][hd]; the 16-byte chunks of
-//   a row are stored at chunk ^ (pos & 7).  A (page, kv head) tile is then one contiguous 32 KB block that the fused decode
-//   step pulls into shared memory with a single cp.async.bulk, and both the mma.sync B-fragment reads of K and the
-//   ldmatrix.trans reads of V are bank-conflict free without padding (kv_tile_offset / kv_chunk_swz in kernels.h).
+//   KV pool layout: ONE pool per layer [page][kv_head][K|V][page_size][hd] fp16, page = block_table[slot][pos / page_size];
+//   the 16-byte chunks of a row are stored at chunk ^ (pos & 7).  A (page, kv head) tile is then one contiguous 32 KB block that
+//   the fused decode step pulls into shared memory with a single cp.async.bulk, and both the mma.sync B-fragment reads of K
+//   and the ldmatrix.trans reads of V are bank-conflict free without padding (kv_tile_offset / kv_chunk_swz in kernels.h).
 // One CTA per token; HBM-bound: reads+writes the qkv row once, writes 2*kvh*hd halves to the pool.
 #include "common.cuh"
 #include "kernels.h"
@@ -16,7 +15,7 @@ namespace {
 
 __global__ void __launch_bounds__(128)
 rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, const float* __restrict__ cos_tab,
-               const float* __restrict__ sin_tab, __half* __restrict__ k_pool, __half* __restrict__ v_pool,
+               const float* __restrict__ sin_tab, __half* __restrict__ kv_pool,
                const int32_t* __restrict__ block_table, const int32_t* __restrict__ slot_ids, int max_pages,
                int page_size) {
   const int tok = blockIdx.x;              // b*S + pos
@@ -38,23 +37,15 @@ rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, cons
     p[d] = ra;
     p[d + hh] = rb;
     if (h >= heads) {
-      if (v_pool != nullptr) {
-        __half* kd = k_pool + ((static_cast<int64_t>(page) * kvh + (h - heads)) * page_size + poff) * hd;
-        kd[d] = ra;
-        kd[d + hh] = rb;
-      } else {
-        __half* kd = k_pool + kv_tile_offset(page, kvh, h - heads, 0, page_size, hd) + static_cast<int64_t>(poff) * hd;
-        kd[kv_chunk_swz(d, poff)] = ra;
-        kd[kv_chunk_swz(d + hh, poff)] = rb;
-      }
+      __half* kd = kv_pool + kv_tile_offset(page, kvh, h - heads, 0, page_size, hd) + static_cast<int64_t>(poff) * hd;
+      kd[kv_chunk_swz(d, poff)] = ra;
+      kd[kv_chunk_swz(d + hh, poff)] = rb;
     }
   }
   const __half* vsrc = row + (heads + kvh) * hd;
   for (int i = threadIdx.x; i < kvh * hd / 8; i += blockDim.x) {
     const int h = (i * 8) / hd, d = (i * 8) % hd;
-    __half* vd = (v_pool != nullptr)
-                     ? v_pool + ((static_cast<int64_t>(page) * kvh + h) * page_size + poff) * hd + d
-                     : k_pool + kv_tile_offset(page, kvh, h, 1, page_size, hd) + static_cast<int64_t>(poff) * hd + kv_chunk_swz(d, poff);
+    __half* vd = kv_pool + kv_tile_offset(page, kvh, h, 1, page_size, hd) + static_cast<int64_t>(poff) * hd + kv_chunk_swz(d, poff);
     *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vsrc + i * 8);
   }
 }
@@ -62,12 +53,12 @@ rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, cons
 }  // namespace
 
 int rope_kv_prefill(__half* qkv, int B, int S, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
-                    __half* k_pool, __half* v_pool, const int32_t* block_table, const int32_t* slot_ids, int max_pages,
+                    __half* kv_pool, const int32_t* block_table, const int32_t* slot_ids, int max_pages,
                     int page_size, cudaStream_t stream) {
   TB_CHECK(hd % 8 == 0, "head_dim must be a multiple of 8");
   if (B * S == 0) return 0;
-  rope_kv_kernel<<<B * S, 128, 0, stream>>>(qkv, S, heads, kvh, hd, cos_tab, sin_tab, k_pool, v_pool, block_table,
-                                            slot_ids, max_pages, page_size);
+  rope_kv_kernel<<<B * S, 128, 0, stream>>>(qkv, S, heads, kvh, hd, cos_tab, sin_tab, kv_pool, block_table, slot_ids, max_pages,
+                                            page_size);
   TB_LAUNCH_OK();
   return 0;
 }

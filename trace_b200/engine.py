@@ -23,7 +23,7 @@ EXPORTS = [
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
     "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
-    "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention", "trace_b200_op_attention_tc", "trace_b200_op_gemv",
+    "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention_tc",
 ]
 
 
@@ -81,10 +81,7 @@ def load_library() -> ctypes.CDLL:
                                                  ctypes.POINTER(f32), ctypes.POINTER(f32), vp, vp, vp]
     lib.trace_b200_op_layernorm.argtypes = [vp, vp, vp, f32, vp, i32, i32, vp]
     lib.trace_b200_op_rmsnorm.argtypes = [vp, vp, f32, vp, i32, i32, vp]
-    lib.trace_b200_op_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32,
-                                            f32, vp]
     lib.trace_b200_op_attention_tc.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]
-    lib.trace_b200_op_gemv.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, f32, i32, vp]
     _lib = lib
     return lib
 
@@ -291,37 +288,12 @@ def op_rmsnorm(x, w, eps):
     return out
 
 
-def op_attention(qkv: torch.Tensor, heads: int, kv_heads: int, head_dim: int, causal: bool) -> torch.Tensor:
-    """qkv [B, S, (heads + 2*kv_heads)*head_dim] fused -> out [B, S, heads*head_dim]."""
-    lib = load_library()
-    qkv = _f16c(qkv)
-    B, S, W = qkv.shape
-    qd, kvd = heads * head_dim, kv_heads * head_dim
-    out = torch.empty((B, S, qd), dtype=torch.float16, device=qkv.device)
-    base = qkv.data_ptr()
-    _check(lib.trace_b200_op_attention(base, base + qd * 2, base + (qd + kvd) * 2, out.data_ptr(), S, W, W, qd, S * W, S * W,
-                                       S * qd, heads, heads // kv_heads, B, head_dim, int(causal), head_dim ** -0.5, _stream()))
-    return out
-
-
 def op_attention_tc(qkv: torch.Tensor, heads: int, kv_heads: int, head_dim: int, causal: bool) -> torch.Tensor:
-    """tcgen05/TMEM attention; same contract as op_attention."""
+    """tcgen05/TMEM attention: qkv [B, S, (heads + 2*kv_heads)*head_dim] fused -> out [B, S, heads*head_dim]."""
     lib = load_library()
     qkv = _f16c(qkv)
     B, S, W = qkv.shape
     out = torch.empty((B, S, heads * head_dim), dtype=torch.float16, device=qkv.device)
     _check(lib.trace_b200_op_attention_tc(qkv.data_ptr(), W, out.data_ptr(), S, heads, kv_heads, head_dim, int(causal), B,
                                           head_dim ** -0.5, _stream()))
-    return out
-
-
-def op_gemv(w: torch.Tensor, x: torch.Tensor, gamma=None, eps: float = 0.0, epi: int = 0, out=None) -> torch.Tensor:
-    lib = load_library()
-    w, x = _f16c(w), _f16c(x)
-    N, K = w.shape
-    B = x.shape[0]
-    if out is None:
-        out = torch.empty((B, N // 2 if epi == 2 else N), dtype=torch.float16, device=x.device)
-    _check(lib.trace_b200_op_gemv(w.data_ptr(), x.data_ptr(), out.data_ptr(), B, N, K, 0 if gamma is None else 1, _ptr(gamma),
-                                  eps, epi, _stream()))
     return out
