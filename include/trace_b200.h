@@ -96,6 +96,25 @@ int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, co
 int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new,
                       int eos, int pad, int64_t* ids_out_host, int* n_out, float* logits_out_dev, void* stream);
 
+/* Continuous batching (replaces the serial batch-1 loops of evaluate.py:296-357 / videomme/evaluate.py:348-383).
+ * A batch of `rows` decode rows stays open; requests are admitted into free rows and retired BETWEEN bursts of decode steps, so
+ * rows of different clip length, prompt length, head and budget share every decode step and a finished row's slot in the MMA
+ * is refilled instead of idling until the slowest row of a static batch ends.  Per-row state (position, head, emitted tokens,
+ * budget) lives on the device; an inactive row points at a one-page dummy slot and an all-zero activation row.
+ *   open   : rows in [1,8]; eos / pad as in trace_b200_decode; sampling as set by trace_b200_set_sampling at this moment.
+ *   admit  : prefill of `embeds` [1,S,hidden] into `slot` (allocated with >= S + max_new positions) and the row's first token
+ *            (heads on the prefill's last hidden state; the other rows are not touched).
+ *   step   : n_steps decode steps for all rows (CUDA-graph replays); row_steps_out / finished_out [rows] = tokens emitted so
+ *            far (can exceed the budget by the steps run after it was used up) and the EOS flags.
+ *   read   : the new ids of a row (<= its budget) and its current head.     retire : frees the row (not the KV slot).
+ *   close  : every row must have been retired. */
+int trace_b200_batch_open(trace_b200_ctx* ctx, int rows, int eos, int pad);
+int trace_b200_batch_admit(trace_b200_ctx* ctx, int row, int slot, const void* embeds, int S, int head, int max_new, void* stream);
+int trace_b200_batch_step(trace_b200_ctx* ctx, int n_steps, int32_t* row_steps_out, int32_t* finished_out, void* stream);
+int trace_b200_batch_read(trace_b200_ctx* ctx, int row, int64_t* ids_out, int capacity, int* n_out, int32_t* head_out);
+int trace_b200_batch_retire(trace_b200_ctx* ctx, int row);
+int trace_b200_batch_close(trace_b200_ctx* ctx);
+
 /* Sampling of the following trace_b200_decode calls: HF GenerationMixin._sample with the default logits warpers as
  * scripts/inference/inference.py:62,71-73 drives it (do_sample=True, temperature=0.2; generation_config top_k=50, top_p=1):
  * logits / temperature, keep {z >= k-th largest} (top_k = 0: keep all), softmax, inverse-CDF draw over ascending token ids

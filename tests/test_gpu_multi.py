@@ -1,5 +1,6 @@
 """N=2 on real GPUs (NCCL): the frame-sharded ViT encode + one all-gather must reproduce the single-GPU slot tokens
-bit-exactly (same kernels, same frames, only the partition differs)."""
+bit-exactly (same kernels, same frames, only the partition differs), and `generate_sharded` -- full clips or per-rank frame
+slices -- must return the ids a single GPU generates for the same clips."""
 import os
 import sys
 
@@ -27,7 +28,29 @@ def _worker(rank, world, port, q):
     ref = eng.encode_frames(frames)
     got = encode_frames_sharded(eng, frames, B, T, dist.group.WORLD)
     torch.cuda.synchronize()
-    q.put((rank, bool(torch.equal(ref, got))))
+    ok = bool(torch.equal(ref, got))
+    # config-4 shape at parity size: 3 clips over 2 ranks through the public multi-GPU call, against a single-GPU generate
+    from trace_b200.model import TraceMistralConfig, TraceMistralForCausalLM
+    from trace_b200.parallel import generate_sharded, shard_bounds
+    model = TraceMistralForCausalLM(TraceMistralConfig(d), device=rank, vit_chunk_frames=4, max_prefill_tokens=512, max_ctx=256)
+    model.load_state_dict(dict(synth.iter_state_dict(d, 0)))
+    n_clips, max_new = 3, 12
+    clips, stamps = [], []
+    for b in range(n_clips):
+        px, ts = synth.synthetic_clip(d, T, seed=77 + b, duration_s=40.0 + 3 * b)
+        clips.append(px.cuda())
+        stamps.append(ts)
+    ids = torch.tensor([[1, 17 + b, 300, -201, 29, 31, 37, -205] for b in range(n_clips)], dtype=torch.int64, device="cuda")
+    single = model.generate(ids, attention_mask=torch.ones_like(ids), images_or_videos=clips, modal_list=["video"] * n_clips, video_timestamps=stamps,
+                            heads=[1] * n_clips, do_sample=False, max_new_tokens=max_new, pad_token_id=2).cpu()
+    h1 = [1] * n_clips
+    full = generate_sharded(model, ids, clips, stamps, h1, max_new, dist.group.WORLD, pad_token_id=2)
+    lo, hi = shard_bounds(T, world, rank)
+    h2 = [1] * n_clips
+    sliced = generate_sharded(model, ids, [c[lo:hi].contiguous() for c in clips], stamps, h2, max_new, dist.group.WORLD, pad_token_id=2, local_slices=True)
+    n = min(single.shape[1], full.shape[1])
+    ok = ok and torch.equal(full[:, :n], single[:, :n]) and torch.equal(sliced, full) and h1 == h2
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 

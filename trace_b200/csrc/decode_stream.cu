@@ -898,13 +898,15 @@ __device__ __forceinline__ void finalize_step(const DsParams& p, int ncta, unsig
                                               const Watch& w) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
-  __shared__ int s_feed[GV_MAXB];
+  __shared__ int s_feed[GV_MAXB], s_cont[GV_MAXB];
   __shared__ float s_f[GV_CONS];
   __shared__ int s_w[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const DecodeStreamState& st = p.st;
   const int step = *st.step;
-  const int max_new = st.ctrl[0], eos = st.ctrl[1], pad = st.ctrl[2], do_sample = st.ctrl[3], use_forced = st.ctrl[8];
+  // ctrl: 0 row stride of out_ids / forced, 1 eos, 2 pad, 3 do_sample, 8 use_forced, 9 rows of this launch (bit mask: an admission
+  // launch of the continuous batcher finalizes ONE row and must leave the others -- their state and next embedding -- alone)
+  const int cap = st.ctrl[0], eos = st.ctrl[1], pad = st.ctrl[2], do_sample = st.ctrl[3], use_forced = st.ctrl[8], mask = st.ctrl[9];
   for (int b = 0; b < p.B; ++b) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -924,34 +926,42 @@ __device__ __forceinline__ void finalize_step(const DsParams& p, int ncta, unsig
     for (int k = 0; k < 8; ++k)
       if (s_v[k] > bv || (s_v[k] == bv && s_i[k] < bi)) { bv = s_v[k]; bi = s_i[k]; }
     cons_sync();
+    const bool in_launch = (mask >> b) & 1;
+    const int rs = st.row_step[b];                        // tokens this row has emitted so far
     int tok = bi;
-    if (do_sample && !st.finished[b]) {
+    if (in_launch && do_sample && !st.finished[b]) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");     // the candidate lines were released after the logits stores
-      tok = sample_row(p, b, s_hlo[b], s_hhi[b], bv, step, s_f, s_w);
+      tok = sample_row(p, b, s_hlo[b], s_hhi[b], bv, rs, s_f, s_w);
     }
     if (tid == 0) {
-      if (st.finished[b]) tok = pad;                       // finished rows keep emitting pad (HF generation loop)
-      if (step < max_new) st.out_ids[static_cast<int64_t>(b) * max_new + step] = tok;
-      const int feed = (use_forced && !st.finished[b] && step < max_new) ? static_cast<int>(st.forced[static_cast<int64_t>(b) * max_new + step]) : tok;
-      if (!st.finished[b] && feed == eos) st.finished[b] = 1;
+      int feed = -1;
+      if (in_launch) {
+        const int budget = st.row_max[b];
+        if (st.finished[b]) tok = pad;                     // finished rows keep emitting pad (HF generation loop)
+        if (rs < budget) st.out_ids[static_cast<int64_t>(b) * cap + rs] = tok;
+        feed = (use_forced && !st.finished[b] && rs < budget) ? static_cast<int>(st.forced[static_cast<int64_t>(b) * cap + rs]) : tok;
+        if (!st.finished[b] && feed == eos) st.finished[b] = 1;
+        st.row_step[b] = rs + 1;
+        s_cont[b] = rs + 1 < budget;
+      }
       s_feed[b] = feed;
     }
     cons_sync();
   }
   if (tid == 0) {
-    int all = 1;
-    for (int b = 0; b < p.B; ++b) all &= st.finished[b];
-    // the head switch happens in prepare_inputs_for_generation (trace_mistral.py:336-344), i.e. only for tokens that are
-    // fed back: not after the last token of the budget and not once every row has finished
-    const bool fed_back = !all && step + 1 < max_new;
+    int all = 1;                                           // every row has hit EOS or used up its budget
+    for (int b = 0; b < p.B; ++b) all &= (st.finished[b] || st.row_step[b] >= st.row_max[b]) ? 1 : 0;
     for (int b = 0; b < p.B; ++b) {
       const int tok = s_feed[b];
-      if (fed_back && st.heads[b] >= 0) {
+      if (tok < 0) continue;
+      // the head switch happens in prepare_inputs_for_generation (trace_mistral.py:336-344), i.e. only for tokens that are
+      // fed back: not after the last token of the budget and not once every row has finished
+      if (!all && s_cont[b] && st.heads[b] >= 0) {
         if (tok == p.vocab) st.heads[b] = 1;
         else if (tok == p.vocab + 1) st.heads[b] = 2;
         else if (tok == p.vocab + 14) st.heads[b] = 0;
       }
-      if (p.advance) st.pos[b] += 1;
+      if (p.advance && s_cont[b]) st.pos[b] += 1;          // a row out of budget stays where it is (its KV slot is full)
     }
     *st.step = step + 1;
     if (all && *st.done_step == 0) *st.done_step = step + 1;
@@ -960,6 +970,7 @@ __device__ __forceinline__ void finalize_step(const DsParams& p, int ncta, unsig
   // next-step input embedding (trace_arch.py:349-373): id % vocab text row, overwritten by the sync / time / score rows
   for (int b = 0; b < p.B; ++b) {
     const int tok = s_feed[b];
+    if (tok < 0) continue;
     const __half* src;
     if (tok == p.vocab) src = p.sync_tab;
     else if (tok > p.vocab && tok < p.vocab + 14) src = p.time_tab + static_cast<size_t>(tok - p.vocab - 1) * p.H;

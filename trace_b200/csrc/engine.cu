@@ -116,6 +116,13 @@ struct trace_b200_ctx {
   uint64_t seed = 0;
   std::vector<int64_t> forced_host;
   int forced_B = 0, forced_n = 0;
+  // continuous batching (trace_b200_batch_*): an open batch of `batch_rows` decode rows, rows admitted / retired between bursts
+  int32_t* d_prefill_slots = nullptr;   // slot ids of the running prefill (its own array: a prefill may run while a batch is open)
+  int batch_rows = 0;                   // 0 = no batch open
+  int batch_eos = 2, batch_pad = 2;
+  int batch_dummy_slot = -1;            // KV slot (1 page) the inactive rows point at
+  std::vector<int> batch_slot;          // slot of every row, -1 = free
+  std::vector<int> batch_budget;
 };
 
 namespace {
@@ -241,7 +248,8 @@ int allocate_all(trace_b200_ctx* ctx) {
   if (dalloc(ctx, &ctx->sst.pos, kMaxB, true) || dalloc(ctx, &ctx->sst.heads, kMaxB, true) ||
       dalloc(ctx, &ctx->sst.finished, kMaxB, true) || dalloc(ctx, &ctx->sst.step, 1, true) ||
       dalloc(ctx, &ctx->sst.done_step, 1, true) || dalloc(ctx, &ctx->sst.out_ids, static_cast<size_t>(kMaxB) * c.max_ctx, true) ||
-      dalloc(ctx, &ctx->sst.slot_ids, kMaxB, true))
+      dalloc(ctx, &ctx->sst.slot_ids, kMaxB, true) || dalloc(ctx, &ctx->sst.row_step, kMaxB, true) ||
+      dalloc(ctx, &ctx->sst.row_max, kMaxB, true) || dalloc(ctx, &ctx->d_prefill_slots, kMaxB, true))
     return 1;
   if (getenv("TRACE_B200_MEGA_TIMING") != nullptr && dalloc(ctx, &ctx->d_dbg, static_cast<size_t>(2) * c.layers * 32 + static_cast<size_t>(ctx->num_sms) * 32, true)) return 1;
   {
@@ -470,10 +478,11 @@ int decode_step(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, c
 int decode_loop(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new, int eos, int pad,
               int64_t* ids_out_host, int* n_out, float* logits_out_dev, cudaStream_t s) {
   const trace_b200_config& c = ctx->c;
-  std::vector<int32_t> pos(B), zeros(kMaxB, 0);
+  TB_CHECK(ctx->batch_rows == 0, "a continuous batch is open on this context (trace_b200_batch_close first)");
+  std::vector<int32_t> pos(B), zeros(kMaxB, 0), budget(kMaxB, max_new);
   for (int b = 0; b < B; ++b) pos[b] = ctx->slot_len[slots_host[b]];
   int32_t ctrl[16] = {0};
-  ctrl[0] = max_new; ctrl[1] = eos; ctrl[2] = pad; ctrl[3] = ctx->do_sample;
+  ctrl[0] = max_new; ctrl[1] = eos; ctrl[2] = pad; ctrl[3] = ctx->do_sample; ctrl[9] = (1 << B) - 1;
   memcpy(&ctrl[4], &ctx->temperature, 4);
   ctrl[5] = ctx->top_k; ctrl[6] = static_cast<int32_t>(ctx->seed & 0xffffffffu); ctrl[7] = static_cast<int32_t>(ctx->seed >> 32);
   const bool forced = !ctx->forced_host.empty();
@@ -494,6 +503,8 @@ int decode_loop(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* 
   TB_CUDA(cudaMemcpyAsync(ctx->sst.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.heads, heads_inout_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.finished, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.row_step, zeros.data(), B * 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.row_max, budget.data(), B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.done_step, zeros.data(), 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaStreamSynchronize(s));     // ctrl / pos / forced_host are host stack or heap memory
@@ -727,8 +738,16 @@ int trace_b200_free_slot(trace_b200_ctx* ctx, int slot) {
   return 0;
 }
 
+static int prefill_impl(trace_b200_ctx* ctx, const int32_t* slots_host, int B, const void* embeds, int S, void* hidden_out, int x_row0,
+                        void* stream);
 int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, const void* embeds, int S, void* hidden_out,
                        void* stream) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows == 0, "a continuous batch is open on this context: rows are prefilled by trace_b200_batch_admit");
+  return prefill_impl(ctx, slots_host, B, embeds, S, hidden_out, 0, stream);
+}
+// x_row0: first row of the decode activation buffer that receives the last hidden states (a row admitted into a running batch)
+static int prefill_impl(trace_b200_ctx* ctx, const int32_t* slots_host, int B, const void* embeds, int S, void* hidden_out, int x_row0,
+                        void* stream) {
   TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
   TB_CHECK(slots_host && embeds && B >= 1 && B <= kMaxB && S >= 1, "bad arguments");
   const trace_b200_config& c = ctx->c;
@@ -742,13 +761,14 @@ int trace_b200_prefill(trace_b200_ctx* ctx, const int32_t* slots_host, int B, co
     TB_CHECK(static_cast<int>(ctx->slot_pages[sl].size()) * kPage >= S, "slot too small for the prompt");
     ctx->slot_len[sl] = S;
   }
-  TB_CUDA(cudaMemcpyAsync(ctx->sst.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
+  TB_CHECK(x_row0 >= 0 && x_row0 + B <= kMaxB, "bad decode row");
+  TB_CUDA(cudaMemcpyAsync(ctx->d_prefill_slots, slots_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->p_h, embeds, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
-  if (decoder_layers_prefill(ctx, B, S, ctx->sst.slot_ids, s)) return 1;
+  if (decoder_layers_prefill(ctx, B, S, ctx->d_prefill_slots, s)) return 1;
   if (hidden_out != nullptr)
     TB_CUDA(cudaMemcpyAsync(hidden_out, ctx->p_h, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
   // last position of every row -> decode activation buffer
-  TB_CUDA(cudaMemcpy2DAsync(ctx->d_x, static_cast<size_t>(c.hidden) * 2, ctx->p_h + static_cast<size_t>(S - 1) * c.hidden,
+  TB_CUDA(cudaMemcpy2DAsync(ctx->d_x + static_cast<size_t>(x_row0) * c.hidden, static_cast<size_t>(c.hidden) * 2, ctx->p_h + static_cast<size_t>(S - 1) * c.hidden,
                             static_cast<size_t>(S) * c.hidden * 2, static_cast<size_t>(c.hidden) * 2, B, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
@@ -773,6 +793,151 @@ int trace_b200_decode(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int
   }
   TB_CHECK(max_new <= c.max_ctx, "max_new exceeds the output buffer");
   return decode_loop(ctx, slots_host, B, heads_inout_host, max_new, eos, pad, ids_out_host, n_out, logits_out_dev, s);
+}
+
+// ---- continuous batching -------------------------------------------------------------------------------------------------
+namespace {
+int batch_ctrl(trace_b200_ctx* ctx, int eos, int pad, int mask, cudaStream_t s) {
+  int32_t ctrl[16] = {0};
+  ctrl[0] = ctx->c.max_ctx; ctrl[1] = eos; ctrl[2] = pad; ctrl[3] = ctx->do_sample; ctrl[9] = mask;
+  memcpy(&ctrl[4], &ctx->temperature, 4);
+  ctrl[5] = ctx->top_k; ctrl[6] = static_cast<int32_t>(ctx->seed & 0xffffffffu); ctrl[7] = static_cast<int32_t>(ctx->seed >> 32);
+  TB_CUDA(cudaMemcpyAsync(ctx->d_ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+int set_row(trace_b200_ctx* ctx, int row, int slot, int pos, int head, int finished, int budget, cudaStream_t s) {
+  const int32_t v[6] = {slot, pos, head, finished, 0, budget};
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.slot_ids + row, &v[0], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.pos + row, &v[1], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.heads + row, &v[2], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.finished + row, &v[3], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.row_step + row, &v[4], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.row_max + row, &v[5], 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+}  // namespace
+
+int trace_b200_batch_open(trace_b200_ctx* ctx, int rows, int eos, int pad) {
+  TB_CHECK(ctx != nullptr && ctx->finalized, "context not finalized");
+  TB_CHECK(rows >= 1 && rows <= kMaxB, "a decode batch has 1..8 rows");
+  TB_CHECK(ctx->batch_rows == 0, "a batch is already open");
+  TB_CUDA(cudaSetDevice(ctx->device));
+  int dummy = -1;
+  if (trace_b200_alloc_slot(ctx, 1, &dummy)) return 1;
+  cudaStream_t s = ctx->dstream;
+  ctx->batch_dummy_slot = dummy;
+  ctx->batch_slot.assign(rows, -1);
+  ctx->batch_budget.assign(rows, 0);
+  ctx->batch_eos = eos;
+  ctx->batch_pad = pad;
+  const int32_t zero = 0;
+  TB_CUDA(cudaMemsetAsync(ctx->d_x, 0, static_cast<size_t>(kMaxB) * ctx->c.hidden * 2, s));   // inactive rows: x = 0 -> every projection of them is 0
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.step, &zero, 4, cudaMemcpyHostToDevice, s));
+  TB_CUDA(cudaMemcpyAsync(ctx->sst.done_step, &zero, 4, cudaMemcpyHostToDevice, s));
+  for (int r = 0; r < rows; ++r)
+    if (set_row(ctx, r, dummy, 0, 0, 1, 0, s)) return 1;                                          // finished, budget 0: never advances, never emits
+  ctx->batch_rows = rows;
+  return 0;
+}
+
+int trace_b200_batch_admit(trace_b200_ctx* ctx, int row, int slot, const void* embeds, int S, int head, int max_new, void* stream) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows > 0, "no batch open");
+  TB_CHECK(row >= 0 && row < ctx->batch_rows && ctx->batch_slot[row] < 0, "row is not free");
+  TB_CHECK(slot >= 0 && slot < kMaxSlots && ctx->slot_used[slot] && slot != ctx->batch_dummy_slot, "bad KV slot");
+  TB_CHECK(max_new >= 1 && S + max_new <= static_cast<int>(ctx->slot_pages[slot].size()) * kPage && S + max_new <= ctx->c.max_ctx,
+           "slot too small for prompt + max_new tokens");
+  TB_CHECK(head >= -1 && head <= 2, "head id must be -1, 0, 1 or 2");
+  NvtxRange nvtx("trace_b200.batch_admit");
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int32_t sl = slot;
+  if (prefill_impl(ctx, &sl, 1, embeds, S, nullptr, row, stream)) return 1;
+  TB_CUDA(cudaEventRecord(ctx->ev_in, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = ctx->dstream;
+  TB_CUDA(cudaStreamWaitEvent(s, ctx->ev_in, 0));
+  if (set_row(ctx, row, slot, S, head, 0, max_new, s)) return 1;
+  if (batch_ctrl(ctx, ctx->batch_eos, ctx->batch_pad, 1 << row, s)) return 1;
+  // the row's first token: heads on the prefill's last hidden state; only this row is finalized
+  if (decode_step(ctx, ctx->batch_rows, 0, nullptr, s)) return 1;
+  ++ctx->launches_since_reset;
+  TB_CUDA(cudaStreamSynchronize(s));
+  ctx->batch_slot[row] = slot;
+  ctx->batch_budget[row] = max_new;
+  return 0;
+}
+
+int trace_b200_batch_step(trace_b200_ctx* ctx, int n_steps, int32_t* row_steps_out, int32_t* finished_out, void* stream) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows > 0 && n_steps >= 1 && row_steps_out && finished_out, "bad arguments / no batch open");
+  (void)stream;
+  NvtxRange nvtx("trace_b200.batch_step");
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int B = ctx->batch_rows;
+  cudaStream_t s = ctx->dstream;
+  if (batch_ctrl(ctx, ctx->batch_eos, ctx->batch_pad, (1 << B) - 1, s)) return 1;
+  cudaGraphExec_t exec = nullptr;
+  auto it = ctx->graphs.find(B);
+  int done_steps = 0;
+  if (it != ctx->graphs.end()) {
+    exec = it->second;
+  } else {
+    if (decode_step(ctx, B, ctx->c.layers, nullptr, s)) return 1;      // eager once (kernel attributes), then capture
+    ++done_steps;
+    cudaGraph_t graph = nullptr;
+    TB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = ctx->launches;
+    const int rc = decode_step(ctx, B, ctx->c.layers, nullptr, s);
+    ctx->launches = before;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    TB_CHECK(rc == 0, std::string("decode step failed during graph capture: ") + tb::get_error());
+    TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->graphs[B] = exec;
+  }
+  for (; done_steps < n_steps; ++done_steps) TB_CUDA(cudaGraphLaunch(exec, s));
+  ctx->launches += n_steps;
+  ctx->launches_since_reset += n_steps;
+  TB_CUDA(cudaMemcpyAsync(row_steps_out, ctx->sst.row_step, B * 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaMemcpyAsync(finished_out, ctx->sst.finished, B * 4, cudaMemcpyDeviceToHost, s));
+  cudaError_t e = cudaStreamSynchronize(s);
+  TB_CHECK(e == cudaSuccess && *ctx->h_err == 0, std::string("decode step failed: ") + cudaGetErrorString(e) + " (watchdog word " + std::to_string(*ctx->h_err) + ")");
+  return 0;
+}
+
+int trace_b200_batch_read(trace_b200_ctx* ctx, int row, int64_t* ids_out, int capacity, int* n_out, int32_t* head_out) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows > 0 && row >= 0 && row < ctx->batch_rows && ctx->batch_slot[row] >= 0, "row is not active");
+  TB_CHECK(ids_out && n_out && head_out, "null argument");
+  cudaStream_t s = ctx->dstream;
+  int32_t st = 0;
+  TB_CUDA(cudaMemcpyAsync(&st, ctx->sst.row_step + row, 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaMemcpyAsync(head_out, ctx->sst.heads + row, 4, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  const int n = st < ctx->batch_budget[row] ? st : ctx->batch_budget[row];
+  TB_CHECK(capacity >= n, "ids buffer too small");
+  TB_CUDA(cudaMemcpyAsync(ids_out, ctx->sst.out_ids + static_cast<size_t>(row) * ctx->c.max_ctx, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
+  TB_CUDA(cudaStreamSynchronize(s));
+  *n_out = n;
+  return 0;
+}
+
+int trace_b200_batch_retire(trace_b200_ctx* ctx, int row) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows > 0 && row >= 0 && row < ctx->batch_rows && ctx->batch_slot[row] >= 0, "row is not active");
+  if (set_row(ctx, row, ctx->batch_dummy_slot, 0, 0, 1, 0, ctx->dstream)) return 1;
+  TB_CUDA(cudaMemsetAsync(ctx->d_x + static_cast<size_t>(row) * ctx->c.hidden, 0, static_cast<size_t>(ctx->c.hidden) * 2, ctx->dstream));
+  TB_CUDA(cudaStreamSynchronize(ctx->dstream));
+  ctx->batch_slot[row] = -1;
+  ctx->batch_budget[row] = 0;
+  return 0;
+}
+
+int trace_b200_batch_close(trace_b200_ctx* ctx) {
+  TB_CHECK(ctx != nullptr && ctx->batch_rows > 0, "no batch open");
+  for (int r = 0; r < ctx->batch_rows; ++r) TB_CHECK(ctx->batch_slot[r] < 0, "retire every row before closing the batch");
+  if (trace_b200_free_slot(ctx, ctx->batch_dummy_slot)) return 1;
+  ctx->batch_dummy_slot = -1;
+  ctx->batch_rows = 0;
+  return 0;
 }
 
 int trace_b200_set_sampling(trace_b200_ctx* ctx, int do_sample, float temperature, int top_k, uint64_t seed) {

@@ -69,9 +69,11 @@ __host__ __device__ inline int kv_chunk_swz(int d, int pos) { return (((d >> 3) 
 // ---- decode_stream.cu : the decode step as one cooperative kernel, one HBM stream (weights + K/V pages), flag-in-data exchanges ----
 struct DecodeStreamState {     // device-resident generation state; nothing in it is baked into a captured graph
   int32_t *pos, *heads, *finished, *step, *done_step;
+  int32_t *row_step, *row_max; // [B] tokens emitted by the row so far / its budget (a row is done at EOS or at its budget)
   int64_t* out_ids;            // [B, ctrl[0]]
   int32_t* slot_ids;           // [B]
-  int32_t* ctrl;               // [16]: 0 max_new, 1 eos, 2 pad, 3 do_sample, 4 temperature (float bits), 5 top_k, 6/7 seed lo/hi, 8 use_forced
+  int32_t* ctrl;               // [16]: 0 row stride of out_ids / forced, 1 eos, 2 pad, 3 do_sample, 4 temperature (float bits), 5 top_k,
+                               //       6/7 seed lo/hi, 8 use_forced, 9 bit mask of the rows this launch finalizes
   const int64_t* forced;       // [B, ctrl[0]] teacher-forced ids (fed back instead of the chosen token when ctrl[8])
 };
 struct DecodeStreamArgs {

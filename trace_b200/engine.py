@@ -22,7 +22,8 @@ EXPORTS = [
     "trace_b200_abi_version", "trace_b200_last_error", "trace_b200_create", "trace_b200_destroy",
     "trace_b200_load_weight", "trace_b200_finalize_weights", "trace_b200_encode_frames",
     "trace_b200_build_prefill", "trace_b200_alloc_slot", "trace_b200_free_slot", "trace_b200_prefill",
-    "trace_b200_decode", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
+    "trace_b200_decode", "trace_b200_batch_open", "trace_b200_batch_admit", "trace_b200_batch_step", "trace_b200_batch_read",
+    "trace_b200_batch_retire", "trace_b200_batch_close", "trace_b200_set_sampling", "trace_b200_set_forced_ids", "trace_b200_decode_plan", "trace_b200_launch_count", "trace_b200_last_decode_timing", "trace_b200_weight_bytes", "trace_b200_debug_timeline", "trace_b200_op_gemm",
     "trace_b200_preprocess_frames", "trace_b200_op_layernorm", "trace_b200_op_rmsnorm", "trace_b200_op_attention_tc",
 ]
 
@@ -67,6 +68,12 @@ def load_library() -> ctypes.CDLL:
     lib.trace_b200_prefill.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), i32, vp, i32, vp, vp]
     lib.trace_b200_decode.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), i32, ctypes.POINTER(ctypes.c_int32), i32, i32,
                                       i32, ctypes.POINTER(i64), ctypes.POINTER(i32), vp, vp]
+    lib.trace_b200_batch_open.argtypes = [vp, i32, i32, i32]
+    lib.trace_b200_batch_admit.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp]
+    lib.trace_b200_batch_step.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp]
+    lib.trace_b200_batch_read.argtypes = [vp, i32, ctypes.POINTER(i64), i32, ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_int32)]
+    lib.trace_b200_batch_retire.argtypes = [vp, i32]
+    lib.trace_b200_batch_close.argtypes = [vp]
     lib.trace_b200_set_sampling.argtypes = [vp, i32, f32, i32, ctypes.c_uint64]
     lib.trace_b200_set_forced_ids.argtypes = [vp, ctypes.POINTER(i64), i32, i32]
     lib.trace_b200_decode_plan.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_int32)]
@@ -227,6 +234,36 @@ class Engine:
         if return_logits:
             return out, logits[: n.value]
         return out
+
+    # ---- continuous batching (include/trace_b200.h: trace_b200_batch_*) ------------------------------------
+    def batch_open(self, rows: int, eos: int = 2, pad: int = 2) -> None:
+        _check(self.lib.trace_b200_batch_open(self._h, rows, eos, pad))
+        self._batch_rows = rows
+
+    def batch_admit(self, row: int, slot: int, embeds: torch.Tensor, head: int, max_new: int) -> None:
+        e = _f16c(embeds)
+        assert e.dim() == 3 and e.shape[0] == 1, "one request per admission: embeds [1,S,hidden]"
+        _check(self.lib.trace_b200_batch_admit(self._h, row, slot, e.data_ptr(), e.shape[1], head, max_new, _stream()))
+
+    def batch_step(self, n_steps: int):
+        """n decode steps for every row; returns (tokens emitted per row, EOS flag per row)."""
+        B = self._batch_rows
+        st, fin = (ctypes.c_int32 * B)(), (ctypes.c_int32 * B)()
+        _check(self.lib.trace_b200_batch_step(self._h, n_steps, st, fin, _stream()))
+        return list(st), list(fin)
+
+    def batch_read(self, row: int, capacity: int):
+        ids = (ctypes.c_int64 * capacity)()
+        n, head = ctypes.c_int(0), ctypes.c_int32(0)
+        _check(self.lib.trace_b200_batch_read(self._h, row, ids, capacity, ctypes.byref(n), ctypes.byref(head)))
+        return torch.tensor(list(ids[: n.value]), dtype=torch.int64), head.value
+
+    def batch_retire(self, row: int) -> None:
+        _check(self.lib.trace_b200_batch_retire(self._h, row))
+
+    def batch_close(self) -> None:
+        _check(self.lib.trace_b200_batch_close(self._h))
+        self._batch_rows = 0
 
     def decode_plan(self, B: int, context_len: int) -> dict:
         out = (ctypes.c_int32 * 8)()

@@ -102,3 +102,81 @@ class BatchScheduler:
             self.stats["batches"] += 1
             self.stats["rows"] += len(rs)
         return results  # type: ignore[return-value]
+
+
+class ContinuousBatcher:
+    """In-flight batching over the engine's `trace_b200_batch_*` calls.
+
+    `BatchScheduler` above forms static buckets: rows of a bucket must share (T, L, max_new) and a bucket decodes until its
+    slowest row ends.  Here ONE decode batch of `rows` rows stays open; a request is prefilled on its own and admitted into
+    whatever row is free, rows of different clip length / prompt length / head / budget share every decode step (the decode
+    kernel keeps position, head, emitted tokens and budget per row on the device), and a row that hits EOS or its budget is read
+    out and refilled between bursts of `burst` steps.  Every distinct clip is encoded once.
+
+    Overlapping the ViT of the next clip with the decode of the current one (the other half of SURVEY §8(f)-4) buys nothing on
+    this design: the decode step is a cooperative kernel that owns all 148 SMs and 219 KB of each SM's shared memory, so kernels
+    of another stream can only run between two steps -- time slicing, not overlap.  What does pay is keeping the 8 batch columns
+    of every weight-streaming MMA occupied, which is what this class does."""
+
+    def __init__(self, model, rows: int = 8, burst: int = 16, eos_token_id: Optional[int] = None, pad_token_id: Optional[int] = None):
+        assert 1 <= rows <= 8 and burst >= 1
+        self.model, self.rows, self.burst = model, rows, burst
+        self.eos = eos_token_id if eos_token_id is not None else model.generation_config.eos_token_id
+        self.pad = pad_token_id if pad_token_id is not None else self.eos
+        self.stats = {"clips_encoded": 0, "admitted": 0, "bursts": 0, "row_steps": 0, "useful_row_steps": 0}
+
+    @torch.no_grad()
+    def run(self, requests: Sequence[ClipRequest]) -> List[ClipResult]:
+        model, eng = self.model, self.model.engine
+        dev = model.device
+        results: List[Optional[ClipResult]] = [None] * len(requests)
+        slot_cache: Dict[int, torch.Tensor] = {}
+        pending = list(range(len(requests)))
+        active: Dict[int, Tuple[int, int]] = {}                # row -> (request index, KV slot)
+        rows = min(self.rows, max(1, len(requests)))
+        eng.batch_open(rows, self.eos, self.pad)
+        try:
+            while pending or active:
+                # ---- admit into free rows ----
+                for row in range(rows):
+                    if row in active or not pending:
+                        continue
+                    i = pending.pop(0)
+                    r = requests[i]
+                    if id(r.clip) not in slot_cache:
+                        slot_cache[id(r.clip)] = model._encode_slots([r.clip])[0]
+                        self.stats["clips_encoded"] += 1
+                    ids = r.input_ids.to(dev, torch.int64).view(1, -1).contiguous()
+                    tid = torch.tensor([frame_time_ids(r.video_timestamps)], dtype=torch.int32, device=dev)
+                    emb = eng.build_prefill(ids, slot_cache[id(r.clip)][None].contiguous(), tid)
+                    S = emb.shape[1]
+                    if S + r.max_new_tokens > eng.max_ctx:
+                        raise RuntimeError(f"prompt ({S}) + max_new_tokens ({r.max_new_tokens}) exceeds the engine context ({eng.max_ctx})")
+                    slot = eng.alloc_slot(S + r.max_new_tokens)
+                    try:
+                        eng.batch_admit(row, slot, emb, -1 if r.head is None else int(r.head), int(r.max_new_tokens))
+                    except Exception:
+                        eng.free_slot(slot)
+                        raise
+                    active[row] = (i, slot)
+                    self.stats["admitted"] += 1
+                # ---- one burst of decode steps for every row ----
+                steps, fin = eng.batch_step(self.burst)
+                self.stats["bursts"] += 1
+                self.stats["row_steps"] += self.burst * rows
+                self.stats["useful_row_steps"] += self.burst * len(active)
+                # ---- read out and retire rows that hit EOS or used up their budget ----
+                for row in list(active):
+                    i, slot = active[row]
+                    if fin[row] or steps[row] >= requests[i].max_new_tokens:
+                        ids_row, head = eng.batch_read(row, int(requests[i].max_new_tokens))
+                        eng.batch_retire(row)
+                        eng.free_slot(slot)
+                        results[i] = ClipResult(trim_after_eos(ids_row, self.eos), None if requests[i].head is None else head, requests[i].tag)
+                        del active[row]
+        finally:
+            for row, (i, slot) in list(active.items()):        # an exception mid-run: leave the engine usable
+                eng.batch_retire(row)
+                eng.free_slot(slot)
+            eng.batch_close()
+        return results  # type: ignore[return-value]
