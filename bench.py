@@ -12,8 +12,10 @@ with the three interleaved heads, through the package's public surface: `TraceMi
              argmax / head switch), HBM-bound: algorithmic bytes per step / mean device time per step measured with CUDA
              events on the engine's decode stream inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
   batched : the batched configurations BASELINE.json names, each with its own roofline --
-             config 3 (one GPU, 8 x 64-frame clips, moment-retrieval prompt) and config 4 (4 x 128-frame clips per GPU;
-             at N GPUs 4N clips through generate_sharded: ViT frame-sharded 128/N frames per GPU + one all-gather).
+             config 3 (one GPU, 8 x 64-frame clips, moment-retrieval prompt), config 4 (4 x 128-frame clips per GPU; at N GPUs
+             4N clips through generate_sharded: ViT frame-sharded 128/N frames per GPU + one all-gather) and config 5 per GPU
+             (mixed 64 / 128-frame clips, Video-MME multiple-choice prompt, 128 new tokens, ONE open decode batch with
+             in-flight admission: trace_b200.serving.ContinuousBatcher).
   cpu_baseline : the CPU oracle (port of the reference path) timed on the host cores on a bounded sample.
 
 N > 1 (torchrun, one rank per GPU, NCCL): one clip per rank per step (weak scaling).  Every clip's 128 frames are split
@@ -77,7 +79,14 @@ def bench_prompt_ids(T, task="dvc"):
     from trace_b200 import prompts, synth
     from trace_b200.conversation import conv_templates
     from trace_b200.mm_utils import tokenizer_MMODAL_token_all
-    text = prompts.DVC if task == "dvc" else prompts.MR.format("a person opens the door and walks into the room")
+    if task == "dvc":
+        text = prompts.DVC
+    elif task == "mr":
+        text = prompts.MR.format("a person opens the door and walks into the room")
+    else:                                             # Video-MME multiple choice (videomme/evaluate.py:259-268, 352-359)
+        from trace_b200.eval.videomme import qa_template
+        text = qa_template({"question": "What does the person do after entering the room?", "answer": "B",
+                            "options": ["A. Sits down.", "B. Opens the window.", "C. Leaves again.", "D. Turns on the light."]})[0]
     conv = conv_templates["llama_2"].copy()
     conv.append_message(conv.roles[0], "<video>\n" + text)
     conv.append_message(conv.roles[1], None)
@@ -427,6 +436,41 @@ def run_b200(args):
                              "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "bytes_per_step": bytes_step,
                              "ms_per_decode_step": step_ms, "traffic": None}}
 
+    def config5_record():
+        """Mixed batch through the continuous batcher: 6 x 64-frame + 6 x 128-frame clips, MCQ prompt, 128 new tokens each
+        (videomme/evaluate.py:380), 8 decode rows: the last 4 requests are admitted into rows as they free up."""
+        from trace_b200.serving import ClipRequest, ContinuousBatcher
+        n_req, new5 = 12, 128
+        ids5 = torch.tensor(bench_prompt_ids(T, "mcq"), dtype=torch.int64)
+        host = []
+        for k in range(n_req):
+            frames = T3 if k % 2 == 0 else T
+            px, ts = synth.synthetic_clip(d, frames, seed=5000 + k)
+            host.append((px.pin_memory(), ts))
+        h2d = sum(px.numel() * 2 for px, _ in host) + n_req * ids5.numel() * 8
+
+        def once():
+            reqs = [ClipRequest(ids5, px.cuda(non_blocking=True), ts, head=1, max_new_tokens=new5, tag=k) for k, (px, ts) in enumerate(host)]
+            sched = ContinuousBatcher(model, rows=8, burst=16)
+            return sched.run(reqs), sched.stats
+
+        once()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res, stats = once()
+        b.record()
+        torch.cuda.synchronize()
+        ms_run = a.elapsed_time(b)
+        tok = sum(r.ids.numel() for r in res)
+        ev = sum(count_events(r.ids.tolist(), d.vocab) for r in res)
+        return {"workload": (f"config 5 per GPU: {n_req} requests, alternating {T3}- and {T}-frame clips, Video-MME multiple-choice prompt, greedy "
+                             f"{new5} new tokens each, one open decode batch of 8 rows with in-flight admission (ContinuousBatcher)"),
+                "requests": n_req, "value": n_req / (ms_run * 1e-3), "unit": "requests/s", "ms": ms_run, "tokens_per_s": tok / (ms_run * 1e-3),
+                "events_per_s": ev / (ms_run * 1e-3), "h2d_bytes": h2d,
+                "measured": "end to end from pinned host memory through ContinuousBatcher.run, device time (CUDA events)",
+                "row_occupancy": stats["useful_row_steps"] / max(stats["row_steps"], 1), "scheduler": stats}
+
     batched_out = {}
     if batched:
         if world == 1:
@@ -434,6 +478,7 @@ def run_b200(args):
             batched_out["config3"] = batched_record("config3", wl3, B3, f"config 3: 1 GPU, batch of {B3} x {T3}-frame clips, moment-retrieval prompt "
                                                     f"(S={S3}), greedy {max_new} new tokens per row")
             del wl3
+            batched_out["config5"] = config5_record()
         wl4 = make_workload(B4 * world, T, "dvc", 8765)
         batched_out["config4"] = batched_record(
             "config4", wl4, B4, (f"config 4 per GPU: {B4} x {T}-frame clips per GPU ({B4 * world} clips on {world} GPU(s)); "

@@ -170,3 +170,29 @@ def test_prefill_groups_respect_the_workspace(model):
     model.engine.max_prefill_tokens = 40
     with pytest.raises(tm.TraceB200Error):
         model.generate(ids, images_or_videos=clips, video_timestamps=ts, heads=[1] * 6, max_new_tokens=3)
+
+
+def test_package_infer_passes_real_timestamps(model, monkeypatch):
+    """trace_b200.infer / x_infer (trace/__init__.py:23-86): text-head-only generate.  The per-frame timestamps that
+    process_video returned must reach generate (they become the time rows of the prompt); fabricating them is an error."""
+    import trace_b200
+    seen = {}
+
+    def fake_generate(ids, **kw):
+        seen.update(kw)
+        seen["ids"] = ids
+        return torch.tensor([[5, 6, 2]])
+
+    monkeypatch.setattr(model, "generate", fake_generate)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    tok = synth.StandInTokenizer()
+    d = synth.tiny_dims(4)
+    video = torch.zeros(4, 3, d.image_size, d.image_size)
+    ts = [[0.0], [1.7], [3.4], [5.1]]
+    out = trace_b200.infer(model, (video, ts), "What happens?", tok)
+    assert isinstance(out, str) and seen["video_timestamps"] == [ts] and "heads" not in seen
+    assert seen["do_sample"] is False and seen["max_new_tokens"] == 1024 and int((seen["ids"] == -201).sum()) == 1
+    trace_b200.x_infer(video, "Which one?", model, tok, mode="mcqa", do_sample=True, video_timestamps=ts)
+    assert seen["do_sample"] is True and abs(seen["temperature"] - 0.2) < 1e-9 and seen["video_timestamps"] == [ts]
+    with pytest.raises(ValueError):
+        trace_b200.infer(model, video, "What happens?", tok)            # no timestamps: refuse instead of inventing them

@@ -408,11 +408,12 @@ __device__ __forceinline__ void consume_tiles(const DsSmem& m, const __half* xs,
 // chunk j+1 is in flight while chunk j is multiplied, and a late producer of the previous phase only delays the chunk it
 // produces.
 //   batch <= 2 : the slice is polled out of the flag-in-data buffer (one 16-byte unit pair per lane and batch row);
-//   batch >= 4 : lanes acquire the epoch flags of the producer CTAs of the chunk (`need(c, kcol)`), then the warp loads its slice
-//                of the dense buffer with 16-byte loads.
-template <int NBC, bool DENSE, typename Need>
-__device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src_ll, const __half* src_d, const unsigned* flags, Need need, int ncta,
-                                               int K, int KS, int ntile, int B, unsigned epoch, int stages, int& rs, uint32_t& rph, const Watch& w) {
+//   batch >= 4 : the caller has acquired the producers' epoch flags (wait_flags); the warp loads its slice of the dense buffer with
+//                16-byte loads.  (Acquiring only the ~12 producer CTAs of each chunk inside this loop was tried: the per-chunk
+//                predicate evaluation and the blocking polls cost more than they saved -- batch 4: 4.0 -> 4.5 ms per step.)
+template <int NBC, bool DENSE>
+__device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src_ll, const __half* src_d, int K, int KS, int ntile, int B,
+                                               unsigned epoch, int stages, int& rs, uint32_t& rph, const Watch& w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ksw = KS / GV_WARPS;                   // this warp's columns of a chunk
@@ -430,14 +431,6 @@ __device__ __forceinline__ void consume_korder(const DsSmem& m, const uint2* src
   const int l16 = ksw >> 3;                        // dense: 16-byte loads per row of the slice (16 when KS = 1024)
   auto issue = [&](int kcol) {
     if (DENSE) {
-      // producers of this chunk: every lane polls the flags c = lane, lane+32, ... it is responsible for
-      for (int cta = lane; cta < ncta; cta += 32) {
-        if (need(cta, kcol)) {
-          unsigned spins = 0;
-          while (ld_acquire_u32(flags + cta) != epoch) ds_repoll(w, spins, 23);
-        }
-      }
-      __syncwarp();
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
         const int idx = lane + 32 * i, b = idx / l16, j = idx - b * l16;
@@ -1127,23 +1120,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
       if (!pro) {
         // O / down projection: k-outer, chunks multiplied as they arrive (consume_korder)
         stamp(p, l, 10 + type * 2);
-        const int grid = ncta, nsplit = p.nsplit, ncomb = p.ncomb, kvh = p.kvh, items = p.B * p.kvh * p.nsplit, KSc = g.KS, gun = 2 * p.ffn;
-        if (type == 1) {
-          // chunk j of the attention output = kv heads [2j*KS/256 ...): produced by the combiner CTAs of those kv heads
-          consume_korder<NB, DENSE>(m, p.attn_ll, p.attnd, p.fa, [=](int c, int kcol) {
-            if (c >= items) return false;
-            const int split = c % nsplit, kv = (c / nsplit) % kvh;
-            const int e0 = kv * (DS_G * DS_HD);
-            return split < ncomb && e0 < kcol + KSc && e0 + DS_G * DS_HD > kcol;
-          }, ncta, g.K, g.KS, ntile, p.B, epl + 3, p.stages, rs, rph, w);
-        } else {
-          // chunk j of the SwiGLU activations <- gate/up rows [2*kcol, 2*(kcol+KS)): the CTAs that own those rows
-          consume_korder<NB, DENSE>(m, p.act_ll, p.actd, p.fact, [=](int c, int kcol) {
-            int a0, a1;
-            rows_of_cta(gun, 4, c, grid, a0, a1);
-            return a0 < 2 * (kcol + KSc) && a1 > 2 * kcol;
-          }, ncta, g.K, g.KS, ntile, p.B, epl + 5, p.stages, rs, rph, w);
-        }
+        if (DENSE) wait_flags(type == 1 ? p.fa : p.fact, type == 1 ? epl + 3 : epl + 5, ncta, all_ctas, w, 21);
+        consume_korder<NB, DENSE>(m, type == 1 ? p.attn_ll : p.act_ll, type == 1 ? p.attnd : p.actd, g.K, g.KS, ntile, p.B,
+                                  type == 1 ? epl + 3 : epl + 5, p.stages, rs, rph, w);
         cons_sync();
         stamp(p, l, 24 + type);
         epilogue_ll<NB, DENSE>(m, r0, r1, 0, ntile, p.B, 1, p.x_ll, p.xd, p.H >> 1, type == 1 ? epl + 4 : epl + 6, s_res);

@@ -475,6 +475,17 @@ int decode_step(trace_b200_ctx* ctx, int B, int layers_run, float* logits_out, c
   return 0;
 }
 
+// exchange epochs are 32-bit (512 per launch): long before they wrap, clear the buffers and restart the counter
+int epoch_guard(trace_b200_ctx* ctx, cudaStream_t s) {
+  if (ctx->launches_since_reset > (1 << 22)) {
+    static const unsigned one = 1;
+    TB_CUDA(cudaMemsetAsync(ctx->d_exchange, 0, ctx->exchange_bytes, s));
+    TB_CUDA(cudaMemcpyAsync(ctx->d_epoch, &one, 4, cudaMemcpyHostToDevice, s));
+    ctx->launches_since_reset = 0;
+  }
+  return 0;
+}
+
 int decode_loop(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* heads_inout_host, int max_new, int eos, int pad,
               int64_t* ids_out_host, int* n_out, float* logits_out_dev, cudaStream_t s) {
   const trace_b200_config& c = ctx->c;
@@ -491,13 +502,7 @@ int decode_loop(trace_b200_ctx* ctx, const int32_t* slots_host, int B, int32_t* 
     TB_CUDA(cudaMemcpyAsync(ctx->d_forced, ctx->forced_host.data(), ctx->forced_host.size() * 8, cudaMemcpyHostToDevice, s));
     ctrl[8] = 1;
   }
-  // exchange epochs are 32-bit (512 per launch): long before they wrap, clear the buffers and restart the counter
-  if (ctx->launches_since_reset > (1 << 22)) {
-    const unsigned one = 1;
-    TB_CUDA(cudaMemsetAsync(ctx->d_exchange, 0, ctx->exchange_bytes, s));
-    TB_CUDA(cudaMemcpyAsync(ctx->d_epoch, &one, 4, cudaMemcpyHostToDevice, s));
-    ctx->launches_since_reset = 0;
-  }
+  if (epoch_guard(ctx, s)) return 1;
   TB_CUDA(cudaMemcpyAsync(ctx->d_ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.slot_ids, slots_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->sst.pos, pos.data(), B * 4, cudaMemcpyHostToDevice, s));
@@ -874,6 +879,7 @@ int trace_b200_batch_step(trace_b200_ctx* ctx, int n_steps, int32_t* row_steps_o
   TB_CUDA(cudaSetDevice(ctx->device));
   const int B = ctx->batch_rows;
   cudaStream_t s = ctx->dstream;
+  if (epoch_guard(ctx, s)) return 1;
   if (batch_ctrl(ctx, ctx->batch_eos, ctx->batch_pad, (1 << B) - 1, s)) return 1;
   cudaGraphExec_t exec = nullptr;
   auto it = ctx->graphs.find(B);
