@@ -6,6 +6,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, free when no tool is attached
@@ -88,6 +89,11 @@ struct trace_b200_ctx {
   // decode graphs, keyed by batch size: nothing that varies between calls (max_new / eos / pad / sampling / forced ids) is a
   // kernel parameter -- it lives in device memory (sst.ctrl)
   std::map<int, cudaGraphExec_t> graphs;
+  // prefill graphs keyed by (B, S): the 32 x 7 launches of the decoder layers only depend on the shapes (workspaces, weights,
+  // KV pool and the slot-id array are context-owned), so a repeated shape replays one graph instead of 224 launches
+  std::map<std::pair<int, int>, cudaGraphExec_t> prefill_graphs;
+  std::map<std::pair<int, int>, int> prefill_seen;
+  int prefill_graph = 1;          // TRACE_B200_PREFILL_GRAPH=0: plain launches
   // decode runs on an engine-owned stream (graph capture is illegal on the legacy default stream)
   cudaStream_t dstream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -258,6 +264,7 @@ int allocate_all(trace_b200_ctx* ctx) {
       return (e != nullptr && atoi(e) >= lo && atoi(e) <= hi) ? atoi(e) : dflt;
     };
     ctx->cooperative = env_int("TRACE_B200_COOP", 0, 1, 1);
+    ctx->prefill_graph = env_int("TRACE_B200_PREFILL_GRAPH", 0, 1, 1);
     ctx->max_stages = env_int("TRACE_B200_STAGES", 0, 8, 0);
     ctx->poll_sleep_ns = env_int("TRACE_B200_POLL_SLEEP", 0, 5000, 0);
     ctx->watchdog_ms = env_int("TRACE_B200_WATCHDOG_MS", 1, 3600000, 4000);    // compute-sanitizer runs need minutes
@@ -634,6 +641,7 @@ void trace_b200_destroy(trace_b200_ctx* ctx) {
   if (ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : ctx->prefill_graphs) cudaGraphExecDestroy(kv.second);
   if (ctx->dstream) cudaStreamDestroy(ctx->dstream);
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -769,7 +777,38 @@ static int prefill_impl(trace_b200_ctx* ctx, const int32_t* slots_host, int B, c
   TB_CHECK(x_row0 >= 0 && x_row0 + B <= kMaxB, "bad decode row");
   TB_CUDA(cudaMemcpyAsync(ctx->d_prefill_slots, slots_host, B * 4, cudaMemcpyHostToDevice, s));
   TB_CUDA(cudaMemcpyAsync(ctx->p_h, embeds, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
-  if (decoder_layers_prefill(ctx, B, S, ctx->d_prefill_slots, s)) return 1;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  const bool graph_ok = ctx->prefill_graph && cap == cudaStreamCaptureStatusNone && s != nullptr && s != cudaStreamLegacy;   // capture is illegal on the legacy default stream
+  const auto key = std::make_pair(B, S);
+  auto it = ctx->prefill_graphs.find(key);
+  if (graph_ok && it != ctx->prefill_graphs.end()) {
+    TB_CUDA(cudaGraphLaunch(it->second, s));
+    ctx->launches += static_cast<int64_t>(c.layers) * 7;
+  } else if (graph_ok && ctx->prefill_seen[key]++ >= 1) {
+    // the shape repeats (a batch of clips with one prompt, the bench): capture the launches once and replay them from now on.
+    // A shape seen for the first time runs eagerly -- drivers with ever-changing prompt lengths never pay for a capture.
+    cudaGraph_t graph = nullptr;
+    TB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = ctx->launches;
+    const int rc = decoder_layers_prefill(ctx, B, S, ctx->d_prefill_slots, s);
+    ctx->launches = before;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    TB_CHECK(rc == 0, std::string("prefill failed during graph capture: ") + tb::get_error());
+    TB_CHECK(ce == cudaSuccess && graph != nullptr, std::string("prefill graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    TB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (ctx->prefill_graphs.size() >= 16) {                                                 // bounded
+      for (auto& kv : ctx->prefill_graphs) cudaGraphExecDestroy(kv.second);
+      ctx->prefill_graphs.clear();
+    }
+    ctx->prefill_graphs[key] = exec;
+    TB_CUDA(cudaGraphLaunch(exec, s));
+    ctx->launches += static_cast<int64_t>(c.layers) * 7;
+  } else if (decoder_layers_prefill(ctx, B, S, ctx->d_prefill_slots, s)) {
+    return 1;
+  }
   if (hidden_out != nullptr)
     TB_CUDA(cudaMemcpyAsync(hidden_out, ctx->p_h, static_cast<size_t>(B) * S * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
   // last position of every row -> decode activation buffer
