@@ -120,6 +120,15 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// named barrier 1 + q (q = 0..3) among 64 threads (two whole warps) of the CTA; immediate ids so that ptxas reserves 5 barriers, not 16
+__device__ __forceinline__ void pair_bar_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() {   // generic-proxy writes -> visible to async proxy (TMA/UMMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
