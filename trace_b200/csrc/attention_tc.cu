@@ -61,7 +61,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
   constexpr int NA = HD / 64;                       // 64-column atoms per head row
   constexpr int Q_BYTES = NA * ATOM_BYTES;
   constexpr int KV_BYTES = NA * ATOM_BYTES;
-  constexpr int TMEM_COLS = 256;                    // S: [0,128)  O: [128, 128+HD)
+  constexpr int P_COL = 128 + HD;                   // P (fp16 pairs): 64 columns
+  constexpr int TMEM_COLS = HD == 64 ? 256 : 512;   // S: [0,128)  O: [128, 128+HD)  P: [128+HD, 192+HD)
   // 1024-byte alignment (SWIZZLE_128B atoms) comes from the declaration, not from a padded request: with the pad the
   // d = 64 instantiation needed 113.1 KB + 1 KB reserved per CTA and exactly missed two CTAs per SM (228 KB)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -70,8 +71,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;                       // 2 stages
   uint8_t* sV = sK + 2 * KV_BYTES;                  // 2 stages
-  uint8_t* sP = sV + 2 * KV_BYTES;                  // 2 atoms (128 keys)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATOM_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * KV_BYTES);
   uint64_t* q_full = bars;                          // [1]
   uint64_t* k_full = bars + 1;                      // [2]
   uint64_t* k_empty = bars + 3;                     // [2]
@@ -159,9 +159,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
         if (lane == 0) {
 #pragma unroll
           for (int kk = 0; kk < AT_BKV / 16; ++kk) {              // 16 keys per MMA
-            const uint64_t ad = umma_desc_sw128(smem_u32(sP + (kk / 4) * ATOM_BYTES)) + 2 * (kk % 4);
             const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV + st * KV_BYTES) + kk * 2048, ATOM_BYTES);
-            umma_f16(tmem_base + 128, ad, bd, idesc_pv, (i > 0 || kk != 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base + 128, tmem_base + P_COL + kk * 8, bd, idesc_pv, (i > 0 || kk != 0) ? 1u : 0u);
           }
           umma_commit(pv_done);
           umma_commit(&v_empty[st]);
@@ -253,54 +252,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       }
       const float ms = (m_run == -INFINITY) ? 0.f : m_run * scale_log2;
       float rs = 0.f;
-      uint8_t* prow = sP + r * 128;
       if (ONE_PASS) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {                            // 8 keys -> one 16-byte chunk of the swizzled row
-          uint32_t pk[4];
+        for (int c = 0; c < 4; ++c) {                             // 32 keys -> 16 columns of fp16 pairs in the row's TMEM lane
+          uint32_t pk[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[(c * 8 + 2 * q) % NV]), scale_log2, -ms));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[(c * 8 + 2 * q + 1) % NV]), scale_log2, -ms));
+          for (int q = 0; q < 16; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[(c * 32 + 2 * q) % NV]), scale_log2, -ms));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[(c * 32 + 2 * q + 1) % NV]), scale_log2, -ms));
             rs += p0 + p1;
             pk[q] = pack_half2(p0, p1);
           }
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          tmem_st_32x16(taddr + P_COL + c * 16, pk);
         }
-      } else {
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-          tmem_ld_32x32(taddr + c2 * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32(taddr + c2 * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
-          tmem_ld_wait();
-          if (c2 == 1) {
-            tc_fence_before();
-            mbar_arrive(s_free);                                  // last read of S(j)
-          }
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const int c = c2 * 8 + cc;
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = kbase + c * 8 + 2 * q;
-              float s0 = __uint_as_float(v[(cc * 8 + 2 * q) % NV]), s1 = __uint_as_float(v[(cc * 8 + 2 * q + 1) % NV]);
-              if (masked) {
-                if (!(col < seqlen && (!CAUSAL || col <= qrow))) s0 = -INFINITY;
-                if (!(col + 1 < seqlen && (!CAUSAL || col + 1 <= qrow))) s1 = -INFINITY;
-              }
-              const float p0 = ex2_approx(fmaf(s0, scale_log2, -ms));
-              const float p1 = ex2_approx(fmaf(s1, scale_log2, -ms));
-              rs += p0 + p1;
-              pk[q] = pack_half2(p0, p1);
-            }
-            *reinterpret_cast<uint4*>(prow + (c >> 3) * ATOM_BYTES + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
+        tmem_st_wait();
       }
       l_run += rs;
       tc_fence_before();
-      fence_proxy_async();                                        // generic-proxy smem writes -> visible to the UMMA
       mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> fp16 ----
@@ -350,7 +318,7 @@ EncodeTiledFn at_encode_fn() {
 template <int HD, bool CAUSAL>
 int launch_tc(const CUtensorMap& tm, __half* O, int seqlen, int o_stride, int64_t o_bstride, int q_col0, int k_col0, int v_col0,
               int heads, int group, int batch, float scale, cudaStream_t stream) {
-  constexpr int SMEM = (HD / 64) * ATOM_BYTES * 5 + 2 * ATOM_BYTES + 128;
+  constexpr int SMEM = (HD / 64) * ATOM_BYTES * 5 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     TB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
