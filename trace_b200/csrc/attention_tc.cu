@@ -200,8 +200,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
             if (!(col < seqlen && (!CAUSAL || col <= qrow))) v[i] = __float_as_uint(-INFINITY);
           }
         }
+        // eight independent chains instead of one of 128 dependent FMNMX (~550 clk of latency per tile with two warps per scheduler)
+        float m8[8];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int k = 0; k < 8; ++k) m8[k] = __uint_as_float(v[k]);
+#pragma unroll
+        for (int i = 8; i < NV; i += 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m8[k] = fmaxf(m8[k], __uint_as_float(v[i + k]));
+        }
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       } else {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
