@@ -33,7 +33,7 @@ def box_hbm_gbs():
 BOX_GBS = box_hbm_gbs()
 d = synth.full_dims(a.frames)
 S = 14 * a.frames + L_TEXT - 1
-model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frames=32, max_prefill_tokens=S * a.batch,
+model = TraceMistralForCausalLM(TraceMistralConfig(d), device=0, vit_chunk_frames=64, max_prefill_tokens=S * a.batch,
                                 max_ctx=S + a.max_new + 64, kv_pages=(a.batch + 1) * ((S + a.max_new + 127) // 64))
 for name, shape, kind in synth.param_specs(d):
     model.engine.load_weight(name, synth.synth_tensor(name, shape, kind, 0, device="cuda"))

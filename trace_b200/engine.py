@@ -115,7 +115,7 @@ class Engine:
     """One context on one device.  Mirrors the life-cycle of the reference model object:
     construct (from_pretrained) -> encode / prefill / decode per generate() call."""
 
-    def __init__(self, dims: synth.TraceDims, device: int = 0, vit_chunk_frames: int = 32,
+    def __init__(self, dims: synth.TraceDims, device: int = 0, vit_chunk_frames: int = 64,
                  max_prefill_tokens: int = 4096, max_ctx: int = 4096, kv_pages: Optional[int] = None):
         if not torch.cuda.is_available():
             raise TraceB200Error("trace_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
