@@ -44,6 +44,11 @@ constexpr int DS_RES_PITCH = 40;                               // residual rows 
 constexpr int DS_THREADS = GV_CONS + 128;
 constexpr int DS_REGS_CONSUMER = 224;
 constexpr int DS_REGS_PRODUCER = 56;
+// words between the epoch flags of two producer CTAs (dense exchange, batch >= 4).  With the flags packed (stride 1) every CTA polls the
+// same five cache lines -- 148 x 148 acquire loads per round into a handful of L2 slices; one flag per 128-byte line spreads them.
+#ifndef DS_FLAG_STRIDE
+#define DS_FLAG_STRIDE 32
+#endif
 
 struct DsLayer {
   const __half *ln1, *qkv_w, *o_w, *ln2, *gateup_w, *down_w;
@@ -196,13 +201,13 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // all 256 consumer threads, after the CTA's stores of the exchange (bar.sync + release: cumulative over the CTA's writes)
 __device__ __forceinline__ void publish(unsigned* flags, int vid, unsigned epoch) {
   cons_sync();
-  if (threadIdx.x == 0) st_release_u32(flags + vid, epoch);
+  if (threadIdx.x == 0) st_release_u32(flags + vid * DS_FLAG_STRIDE, epoch);
 }
 template <typename Pred>
 __device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned epoch, int ncta, Pred need, const Watch& w, int code) {
   if (static_cast<int>(threadIdx.x) < ncta && need(static_cast<int>(threadIdx.x))) {
     unsigned spins = 0;
-    while (ld_acquire_u32(flags + threadIdx.x) != epoch) ds_repoll(w, spins, code);
+    while (ld_acquire_u32(flags + threadIdx.x * DS_FLAG_STRIDE) != epoch) ds_repoll(w, spins, code);
   }
   cons_sync();
 }
@@ -1232,7 +1237,7 @@ size_t decode_stream_exchange_bytes(int H, int qkvw, int qd, int ffn, int num_sm
   put(8, static_cast<size_t>(GV_MAXB) * qkvw * 2);
   put(9, static_cast<size_t>(GV_MAXB) * qd * 2);
   put(10, static_cast<size_t>(GV_MAXB) * ffn * 2);
-  put(11, static_cast<size_t>(4) * num_sms * 4);
+  put(11, static_cast<size_t>(4) * num_sms * 4 * DS_FLAG_STRIDE);
   offs[12] = o;
   return o;
 }
@@ -1352,7 +1357,7 @@ int decode_stream_step(const DecodeStreamArgs& a, cudaStream_t stream) {
   p.cand_ll = reinterpret_cast<uint4*>(ex + offs[6]);
   p.xd = reinterpret_cast<__half*>(ex + offs[7]); p.qkvd = reinterpret_cast<__half*>(ex + offs[8]);
   p.attnd = reinterpret_cast<__half*>(ex + offs[9]); p.actd = reinterpret_cast<__half*>(ex + offs[10]);
-  p.fx = reinterpret_cast<unsigned*>(ex + offs[11]); p.fq = p.fx + a.num_sms; p.fa = p.fq + a.num_sms; p.fact = p.fa + a.num_sms;
+  p.fx = reinterpret_cast<unsigned*>(ex + offs[11]); p.fq = p.fx + a.num_sms * DS_FLAG_STRIDE; p.fa = p.fq + a.num_sms * DS_FLAG_STRIDE; p.fact = p.fa + a.num_sms * DS_FLAG_STRIDE;
   p.cos_tab = a.cos_tab; p.sin_tab = a.sin_tab; p.block_table = a.block_table; p.max_pages = a.max_pages;
   p.logits_out = a.logits_out; p.samp_logits = a.samp_logits;
   p.embed = a.embed; p.time_tab = a.time_tab; p.score_tab = a.score_tab; p.sync_tab = a.sync_tab;
