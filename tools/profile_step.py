@@ -56,6 +56,15 @@ if os.environ.get("TRACE_B200_MEGA_TIMING"):
     # decode_stream.cu stamps per layer: 10+2*type staged, 24+type consumed, 11+2*type epilogue written (type 0 qkv, 1 o, 2 gate/up,
     # 3 down); attention: 20 q ready, 21 K/V tiles done, 22 partials written, 23 combine written, 3 phase left
     tl = model.engine.debug_timeline().double() / 1e3   # us
+    L = tl.shape[1]
+    # whole-step accounting of the last step, CTA 0: entry -> prologue -> layer 0 .. L-1 -> head phase -> candidates -> finalize
+    e = tl[0]
+    t_entry, t_pro = float(e[0, 0]), float(e[0, 1])
+    print(f"step CTA0: previous launch's end -> entry {float(e[0, 2]):.2f} us (launch gap + drain)")
+    print(f"step CTA0: entry->prologue {t_pro - t_entry:.2f} us | prologue->layer0 qkv staged {float(e[0, 10]) - t_pro:.2f} | layer0 {float(e[0, 17] - e[0, 10]):.2f} | "
+          f"layers 1..{L - 1} {float(e[L - 1, 17] - e[0, 17]):.2f} ({float(e[L - 1, 17] - e[0, 17]) / (L - 1):.2f} each) | head: wait x {float(e[L - 1, 18] - e[L - 1, 17]):.2f} "
+          f"stream {float(e[L - 1, 28] - e[L - 1, 18]):.2f} epilogue {float(e[L - 1, 19] - e[L - 1, 28]):.2f} candidates {float(e[L - 1, 29] - e[L - 1, 19]):.2f} "
+          f"finalize {float(e[L - 1, 30] - e[L - 1, 29]):.2f} | entry->end {float(e[L - 1, 30]) - t_entry:.2f} us; CTA77 entry->candidates {float(tl[1, L - 1, 29] - tl[1, 0, 0]):.2f}")
     for c in range(2):
         x = tl[c, 1:-1]            # layers 1 .. L-2 (layer 0 follows the prologue, the last one is overwritten by the head phase)
         prev_dn = tl[c, 0:-2, 17]
@@ -78,6 +87,10 @@ if os.environ.get("TRACE_B200_MEGA_TIMING"):
     pc = pc.double()
     import json as _json
     rec = {"smid": pc[:, 31].long().tolist()}
+    dur = [round(float(v) / 1e3, 1) for v in pc[:, 4]][:a.max_new]
+    gap = [round(float(v) / 1e3, 1) for v in pc[:, 5]][:a.max_new]
+    print("per-step entry->end us:", dur)
+    print("per-step gap before us:", gap)
     t0 = float(pc[:, 10].min())
     for nm, k in (("qkv_staged", 10), ("qkv_done", 24), ("o_staged", 12), ("o_done", 25), ("gu_staged", 14), ("gu_done", 26),
                   ("dn_staged", 16), ("dn_done", 27)):

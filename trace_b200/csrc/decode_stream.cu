@@ -1036,7 +1036,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
     fence_barrier_init();
   }
   const int vid = blockIdx.x;
+  stamp(p, 0, 0);                                               // kernel entry (after the layer table copy was issued)
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.layers > 0)   // slot 2: gap since the previous launch's last stamp
+  {
+    // per-step log in the free slots 4 / 5 of the per-CTA rows: row i = decode step i of the call (gap before it, entry -> end)
+    const unsigned long long gap = p.dbg[0] - p.dbg[static_cast<size_t>(p.layers - 1) * 32 + 30];
+    p.dbg[2] = gap;
+    const int si = *p.st.step;
+    if (si >= 0 && si < static_cast<int>(gridDim.x)) p.dbg[static_cast<size_t>(2) * p.layers * 32 + static_cast<size_t>(si) * 32 + 5] = gap;
+  }
   attn_ctl_init(p, &s_ctl, vid);                                // contains __syncthreads
+  stamp(p, 0, 1);                                               // prologue done: the producer starts streaming
   const int ncta = gridDim.x;
   int ulo = 0x7fffffff, uhi = 0;
   for (int b = 0; b < p.B; ++b) { ulo = min(ulo, s_hlo[b]); uhi = max(uhi, s_hhi[b]); }
@@ -1206,9 +1216,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stream_kernel(const __gr
       }
     }
   }
+  stamp(p, max(p.layers - 1, 0), 29);             // this CTA's candidates are out
   if (vid == 0) {
     cons_sync();
     finalize_step(p, ncta, ep0 + 8u * static_cast<unsigned>(p.layers) + 1, s_hlo, s_hhi, w);
+    stamp(p, max(p.layers - 1, 0), 30);           // next token chosen, next embedding written: the step is over
+    if (p.dbg != nullptr && threadIdx.x == 0 && p.layers > 0) {
+      const int si = *p.st.step - 1;              // finalize advanced the step counter
+      if (si >= 0 && si < static_cast<int>(gridDim.x))
+        p.dbg[static_cast<size_t>(2) * p.layers * 32 + static_cast<size_t>(si) * 32 + 4] = p.dbg[static_cast<size_t>(p.layers - 1) * 32 + 30] - p.dbg[0];
+    }
   }
 }
 
