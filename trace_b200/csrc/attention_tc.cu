@@ -1,5 +1,5 @@
 // Blackwell-native attention forward: softmax(Q K^T * scale) V with both contractions on tcgen05 tensor cores,
-// operands fed by TMA, S = Q K^T and the output accumulator O in TMEM.
+// operands fed by TMA; S = Q K^T, the probabilities P and the output accumulator O all live in TMEM.
 //   * ViT:     HF CLIPAttention (non-causal, 16 heads x 64, n = 577)            -- clip_encoder.py:50
 //   * prefill: HF MistralAttention (causal, GQA 32 q / 8 kv heads x 128)        -- trace_mistral.py:178
 //
@@ -7,16 +7,18 @@
 //   warp 4 : TMA producer -- Q once, then K and V tiles of 128 keys into two 2-stage rings (boxes {64 x 128}, SWIZZLE_128B,
 //            straight out of the fused qkv activation: no transposes, no per-head copies)
 //   warp 5 : UMMA issuer  -- S[128x128] = Q K^T   (tcgen05.mma kind::f16, M=128 N=128, A/B K-major)        -> TMEM cols [0,128)
-//                            O[128xd] += P V      (M=128 N=d K=128; P from smem (K-major), V as an MN-major B operand,
-//                                                  i.e. the [key][d] tile exactly as TMA wrote it)          -> TMEM cols [128,128+d)
+//                            O[128xd] += P V      (M=128 N=d K=128; P as the A operand from TMEM cols [128+d,192+d), V as an
+//                                                  MN-major B operand, i.e. the [key][d] tile exactly as TMA wrote it) -> TMEM cols [128,128+d)
 //            software-pipelined: S(j) is issued as soon as the softmax warps hold S(j-1) in registers, i.e. it runs
-//            under the exponentials of tile j-1; O += P(j-1) V(j-1) follows when P(j-1) is in shared memory.
+//            under the exponentials of tile j-1; O += P(j-1) V(j-1) follows when P(j-1) is in TMEM.
 //   warps 0-3 : softmax (thread = query row): ONE tcgen05.ld of the 128 scores into registers -> release the S buffer ->
 //            running max with LAZY rescale (O and the row sum are only rescaled when the max grows by more than 2^8, so
 //            the accumulator stays in TMEM and is touched by these warps only then and in the epilogue) -> ex2 ->
-//            P (fp16, as the reference rounds softmax before the PV matmul) into the swizzled K-major layout UMMA expects.
-// The d=64 (ViT) instantiation uses 112 KB of smem and 256 TMEM columns, so two CTAs share an SM (the ViT tile loop is
-// only 5 long and exp-bound: the second CTA hides the first one's load / drain bubbles); d=128 runs one CTA per SM.
+//            P (fp16, as the reference rounds softmax before the PV matmul) back into TMEM (tcgen05.st: row = lane, two keys
+//            per 32-bit column), from where the TS form of tcgen05.mma takes it as the A operand.
+// The d=64 (ViT) instantiation uses 80 KB of smem and 256 TMEM columns, so two CTAs share an SM (the ViT tile loop is only 5
+// long: the second CTA hides the first one's load / drain bubbles); d=128 (512 TMEM columns) runs one CTA per SM.
+// Measured bounds and the variants that were tried: DESIGN.md section 5.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -179,54 +181,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       tc_fence_after();
       const int kbase = j * AT_BKV;
       const bool masked = (kbase + AT_BKV > seqlen) || (CAUSAL && kbase + AT_BKV - 1 > q0);
-      // d = 128 runs one CTA per SM and can afford the whole score row in registers (ONE TMEM read); d = 64 shares the SM
-      // between two CTAs (170 registers per thread): two passes over TMEM in 32-column chunks instead of spilling.
-      constexpr bool ONE_PASS = true;
-      constexpr int NV = ONE_PASS ? 128 : 64;
-      uint32_t v[NV];
-      float mx = -INFINITY;
-      if (ONE_PASS) {
+      // the whole score row of the tile in registers: ONE round of tcgen05.ld (168 registers; two CTAs of 192 threads share an SM at d = 64)
+      uint32_t v[128];
+      float mx;
+      {
         tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
-        tmem_ld_32x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64 % NV]));
-        tmem_ld_32x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96 % NV]));
+        tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_32x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+        tmem_ld_32x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_free);                                      // the issuer may overwrite S with tile j+1
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
+          for (int i = 0; i < 128; ++i) {
             const int col = kbase + i;
             if (!(col < seqlen && (!CAUSAL || col <= qrow))) v[i] = __float_as_uint(-INFINITY);
           }
         }
-        // eight independent chains instead of one of 128 dependent FMNMX (~550 clk of latency per tile with two warps per scheduler)
+        // eight independent chains instead of one of 128 dependent FMNMX
         float m8[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) m8[k] = __uint_as_float(v[k]);
 #pragma unroll
-        for (int i = 8; i < NV; i += 8) {
+        for (int i = 8; i < 128; i += 8) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) m8[k] = fmaxf(m8[k], __uint_as_float(v[i + k]));
         }
         mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld_32x32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 % NV]));
-          tmem_ld_wait();
-          if (masked) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-              const int col = kbase + c * 64 + i;
-              if (col < seqlen && (!CAUSAL || col <= qrow)) mx = fmaxf(mx, __uint_as_float(v[i % NV]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i % NV]));
-          }
-        }
       }
       // lazy rescale: keep the old reference maximum unless the new one is more than 2^8 above it (P stays <= 256 in fp16,
       // the row sum and O stay consistent with the reference that was used for every term)
@@ -260,21 +242,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ O,
       }
       const float ms = (m_run == -INFINITY) ? 0.f : m_run * scale_log2;
       float rs = 0.f;
-      if (ONE_PASS) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                             // 32 keys -> 16 columns of fp16 pairs in the row's TMEM lane
-          uint32_t pk[16];
+      for (int c = 0; c < 4; ++c) {                               // 32 keys -> 16 columns of fp16 pairs in the row's TMEM lane
+        uint32_t pk[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[(c * 32 + 2 * q) % NV]), scale_log2, -ms));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[(c * 32 + 2 * q + 1) % NV]), scale_log2, -ms));
-            rs += p0 + p1;
-            pk[q] = pack_half2(p0, p1);
-          }
-          tmem_st_32x16(taddr + P_COL + c * 16, pk);
+        for (int q = 0; q < 16; ++q) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * q]), scale_log2, -ms));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * q + 1]), scale_log2, -ms));
+          rs += p0 + p1;
+          pk[q] = pack_half2(p0, p1);
         }
-        tmem_st_wait();
+        tmem_st_32x16(taddr + P_COL + c * 16, pk);
       }
+      tmem_st_wait();
       l_run += rs;
       tc_fence_before();
       mbar_arrive(p_full);
