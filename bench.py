@@ -435,7 +435,8 @@ def run_b200(args):
                 "ms": ms_run, "tokens_per_s": tok / (ms_run * 1e-3), "events_parsed": ev, "h2d_bytes": wl["h2d"],
                 "roofline": {"bound": "hbm", "kernel": f"decode_stream_kernel<{B_local}> (one launch per generated token per row batch)",
                              "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "bytes_per_step": bytes_step,
-                             "ms_per_decode_step": step_ms, "traffic": None}}
+                             "ms_per_decode_step": step_ms, "traffic": NCU_DRAM.get("batched", {}).get(str(B_local), {}).get("bytes"),
+                             "traffic_source": NCU_DRAM.get("batched", {}).get(str(B_local), {}).get("source")}}
 
     def config5_record():
         """Mixed batch through the continuous batcher: 6 x 64-frame + 6 x 128-frame clips, MCQ prompt, 128 new tokens each
