@@ -72,6 +72,17 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
+// eight halves <-> eight floats (16-byte vectors of fp16 activations / weights)
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]); u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
+  return u;
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {   // streaming 128-bit load, no L1 allocate
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -25,16 +25,6 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]); u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
-  return u;
-}
-
 // mode 0: LayerNorm(w,b)   mode 1: RMSNorm(w)
 template <int MODE>
 __device__ __forceinline__ void norm_row(float (&v)[MAXV][8], int nv, int D, const __half* w, const __half* b,
@@ -103,7 +93,7 @@ __global__ void __launch_bounds__(NT) norm_kernel(const __half* x, int ldx, cons
 template <int MODE, int NV>
 __global__ void __launch_bounds__(256) norm_warp_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ w,
                                                         const __half* __restrict__ b, float eps, __half* __restrict__ out, int ldo, int rows) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   constexpr int D = NV * 256;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
@@ -158,15 +148,17 @@ __global__ void __launch_bounds__(256) norm_warp_kernel(const __half* __restrict
 template <int MODE>
 bool launch_norm_warp(const __half* x, int ldx, const __half* w, const __half* b, float eps, __half* out, int ldo, int rows, int D,
                       cudaStream_t stream) {
-  const int grid = (rows + 7) / 8;
+  // 8 rows (warps) per CTA; a prefill has ~2 k rows, i.e. 1.7 CTAs per SM at 8 -- 2 rows per CTA keep every SM's schedulers fed
+  const int wpc = rows >= 16384 ? 8 : 2;
+  const int grid = (rows + wpc - 1) / wpc;
   switch (D) {
-    case 256: norm_warp_kernel<MODE, 1><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 512: norm_warp_kernel<MODE, 2><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 768: norm_warp_kernel<MODE, 3><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 1024: norm_warp_kernel<MODE, 4><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 1280: norm_warp_kernel<MODE, 5><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 2048: norm_warp_kernel<MODE, 8><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
-    case 4096: norm_warp_kernel<MODE, 16><<<grid, 256, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 256: norm_warp_kernel<MODE, 1><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 512: norm_warp_kernel<MODE, 2><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 768: norm_warp_kernel<MODE, 3><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 1024: norm_warp_kernel<MODE, 4><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 1280: norm_warp_kernel<MODE, 5><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 2048: norm_warp_kernel<MODE, 8><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
+    case 4096: norm_warp_kernel<MODE, 16><<<grid, 32 * wpc, 0, stream>>>(x, ldx, w, b, eps, out, ldo, rows); return true;
     default: return false;
   }
 }

@@ -25,21 +25,34 @@ rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, cons
   const int slot = slot_ids[b];
   const int page = block_table[static_cast<int64_t>(slot) * max_pages + pos / page_size];
   const int poff = pos % page_size;
-  // q and k heads: (heads + kvh) * hd/2 rotation pairs
-  const int npairs = (heads + kvh) * hh;
-  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
-    const int h = i / hh, d = i % hh;
+  // q and k heads: rotation pairs (d, d + hd/2), eight consecutive d per thread (16-byte loads / stores of both halves, cos / sin as
+  // float4 pairs); the arithmetic per element is unchanged: fp32 products, one rounding to fp16
+  const int hh8 = hh / 8;
+  const int nvec = (heads + kvh) * hh8;
+  const float4* ct = reinterpret_cast<const float4*>(cos_tab + static_cast<int64_t>(pos) * hh);
+  const float4* st = reinterpret_cast<const float4*>(sin_tab + static_cast<int64_t>(pos) * hh);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int h = i / hh8, d = (i % hh8) * 8;
     __half* p = row + h * hd;
-    const float a = __half2float(p[d]), c2 = __half2float(p[d + hh]);
-    const float c = cos_tab[static_cast<int64_t>(pos) * hh + d], s = sin_tab[static_cast<int64_t>(pos) * hh + d];
-    const __half ra = __float2half_rn(a * c - c2 * s);
-    const __half rb = __float2half_rn(c2 * c + a * s);
-    p[d] = ra;
-    p[d + hh] = rb;
+    float a[8], c2[8], c[8], sn[8], ra[8], rb[8];
+    unpack8(*reinterpret_cast<const uint4*>(p + d), a);
+    unpack8(*reinterpret_cast<const uint4*>(p + d + hh), c2);
+    *reinterpret_cast<float4*>(&c[0]) = ct[d / 4];
+    *reinterpret_cast<float4*>(&c[4]) = ct[d / 4 + 1];
+    *reinterpret_cast<float4*>(&sn[0]) = st[d / 4];
+    *reinterpret_cast<float4*>(&sn[4]) = st[d / 4 + 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ra[j] = a[j] * c[j] - c2[j] * sn[j];
+      rb[j] = c2[j] * c[j] + a[j] * sn[j];
+    }
+    const uint4 va = pack8(ra), vb = pack8(rb);
+    *reinterpret_cast<uint4*>(p + d) = va;
+    *reinterpret_cast<uint4*>(p + d + hh) = vb;
     if (h >= heads) {
       __half* kd = kv_pool + kv_tile_offset(page, kvh, h - heads, 0, page_size, hd) + static_cast<int64_t>(poff) * hd;
-      kd[kv_chunk_swz(d, poff)] = ra;
-      kd[kv_chunk_swz(d + hh, poff)] = rb;
+      *reinterpret_cast<uint4*>(kd + kv_chunk_swz(d, poff)) = va;
+      *reinterpret_cast<uint4*>(kd + kv_chunk_swz(d + hh, poff)) = vb;
     }
   }
   const __half* vsrc = row + (heads + kvh) * hd;
@@ -55,7 +68,7 @@ rope_kv_kernel(__half* __restrict__ qkv, int S, int heads, int kvh, int hd, cons
 int rope_kv_prefill(__half* qkv, int B, int S, int heads, int kvh, int hd, const float* cos_tab, const float* sin_tab,
                     __half* kv_pool, const int32_t* block_table, const int32_t* slot_ids, int max_pages,
                     int page_size, cudaStream_t stream) {
-  TB_CHECK(hd % 8 == 0, "head_dim must be a multiple of 8");
+  TB_CHECK(hd % 16 == 0, "head_dim must be a multiple of 16");
   if (B * S == 0) return 0;
   rope_kv_kernel<<<B * S, 128, 0, stream>>>(qkv, S, heads, kvh, hd, cos_tab, sin_tab, kv_pool, block_table, slot_ids, max_pages,
                                             page_size);
